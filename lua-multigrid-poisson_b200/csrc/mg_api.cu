@@ -1,0 +1,433 @@
+// mg_api.cu -- C ABI (include/mgpoisson.h) of libmgpoisson.so: context, grid-hierarchy arena
+// (K-f), V-cycle scheduling (reference sequence and fused), CUDA-graph replay, reductions,
+// trace, measurement helpers. No torch types, no exceptions across the boundary.
+//
+// Replaces, in the reference: MultigridCPURaw/MultigridGPU :init, :run, :twoGrid,
+// :inPlaceIterativeSolver (cpu-raw.lua:142-258, gpu.lua:26-373). See the header for the
+// per-function citations.
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/mgpoisson.h"
+#include "mg_engine.cuh"
+
+using namespace mg;
+
+static thread_local std::string g_create_error;
+
+extern "C" {
+
+const char *mg_version(void) { return "mgpoisson-b200 0.1 (sm_100a)"; }
+
+const char *mg_last_error(mg_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
+
+static int create_common(int dim, int size, int real_kind, int smooth, int device, int rank,
+                         int nranks, mg_ctx **out)
+{
+    if (!out) return MG_EINVAL;
+    *out = nullptr;
+    if ((dim != 2 && dim != 3) || size < 1 || (size & (size - 1)) != 0 || size > (1 << 20)) {
+        g_create_error = "mg_create: dim must be 2 or 3 and size a power of two";
+        return MG_EINVAL;
+    }
+    if (real_kind < 0 || real_kind > 2) {
+        g_create_error = "mg_create: bad real_kind";
+        return MG_EINVAL;
+    }
+    mg_ctx *c = new (std::nothrow) mg_ctx();
+    if (!c) return MG_ENOMEM;
+    int rc = c->init(dim, size, real_kind, smooth, device, rank, nranks);
+    if (rc != MG_OK) {
+        g_create_error = c->err;
+        c->release();
+        delete c;
+        return rc;
+    }
+    *out = c;
+    return MG_OK;
+}
+
+int mg_create(int dim, int size, int real_kind, int smooth, int device, mg_ctx **out)
+{
+    return create_common(dim, size, real_kind, smooth, device, 0, 1, out);
+}
+
+int mg_destroy(mg_ctx *ctx)
+{
+    if (!ctx) return MG_OK;
+    ctx->release();
+    delete ctx;
+    return MG_OK;
+}
+
+#define CTX_OR_FAIL(ctx) \
+    if (!(ctx)) return MG_EINVAL; \
+    if ((ctx)->activate() != MG_OK) return MG_ECUDA
+
+int mg_set_mode(mg_ctx *ctx, int mode)
+{
+    CTX_OR_FAIL(ctx);
+    if (mode != MG_MODE_FUSED && mode != MG_MODE_REFSEQ) return ctx->fail(MG_EINVAL, "bad mode");
+    ctx->mode = mode;
+    if (mode == MG_MODE_REFSEQ) return ctx->ensure_debug_arena();
+    return MG_OK;
+}
+
+int mg_set_stream(mg_ctx *ctx, void *cuda_stream)
+{
+    CTX_OR_FAIL(ctx);
+    ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
+    ctx->borrowed_stream = cuda_stream != nullptr;
+    return MG_OK;
+}
+
+int mg_set_tuning(mg_ctx *ctx, int tb, int small_L, int use_graph)
+{
+    CTX_OR_FAIL(ctx);
+    if (tb > 4) return ctx->fail(MG_EINVAL, "tb must be 1..4");
+    if (small_L > (1 << (SMALL_MAX_LEVELS - 1))) return ctx->fail(MG_EINVAL, "small_L too large");
+    if (tb > 0) ctx->tb = tb;
+    if (small_L >= 0) ctx->small_L = small_L;
+    if (use_graph >= 0) ctx->use_graph = use_graph;
+    ctx->drop_graph();
+    return MG_OK;
+}
+
+int mg_get_info(mg_ctx *ctx, int *dim, int *size, int *real_kind, int *smooth, int *nlevels,
+                uint64_t *arena_bytes)
+{
+    if (!ctx) return MG_EINVAL;
+    if (dim) *dim = ctx->dim;
+    if (size) *size = ctx->size;
+    if (real_kind) *real_kind = ctx->real_kind;
+    if (smooth) *smooth = ctx->smooth;
+    if (nlevels) *nlevels = ctx->nlevels;
+    if (arena_bytes) *arena_bytes = ctx->arena_bytes + ctx->debug_arena_bytes;
+    return MG_OK;
+}
+
+int mg_init_cells(mg_ctx *ctx)
+{
+    CTX_OR_FAIL(ctx);
+    int rc = ctx->eng->init_cells(ctx);
+    if (rc) return rc;
+    return ctx->sync();
+}
+
+int mg_zero_corrections(mg_ctx *ctx)
+{
+    CTX_OR_FAIL(ctx);
+    for (int lv = 0; lv < ctx->nlevels; ++lv)
+        if (ctx->V[lv]) MG_CK(ctx, cudaMemsetAsync(ctx->V[lv], 0, ctx->level_bytes(lv), ctx->stream));
+    return ctx->sync();
+}
+
+void *mg_device_ptr(mg_ctx *ctx, int which, int level)
+{
+    if (!ctx) return nullptr;
+    return ctx->buffer(which, level, nullptr);
+}
+
+int mg_upload(mg_ctx *ctx, int which, int level, const void *host, size_t bytes)
+{
+    CTX_OR_FAIL(ctx);
+    size_t cap = 0;
+    if (which >= MG_BUF_ERRORBUF && ctx->ensure_debug_arena() != MG_OK) return MG_ENOMEM;
+    void *d = ctx->buffer(which, level, &cap);
+    if (!d || !host) return ctx->fail(MG_EINVAL, "mg_upload: no such buffer");
+    if (bytes > cap) return ctx->fail(MG_EINVAL, "mg_upload: too many bytes");
+    MG_CK(ctx, cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    return ctx->sync();
+}
+
+int mg_download(mg_ctx *ctx, int which, int level, void *host, size_t bytes)
+{
+    CTX_OR_FAIL(ctx);
+    size_t cap = 0;
+    void *d = ctx->buffer(which, level, &cap);
+    if (!d || !host) return ctx->fail(MG_EINVAL, "mg_download: buffer not materialised");
+    if (bytes > cap) return ctx->fail(MG_EINVAL, "mg_download: too many bytes");
+    MG_CK(ctx, cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    return ctx->sync();
+}
+
+void *mg_host_alloc(size_t bytes)
+{
+    void *p = nullptr;
+    if (cudaMallocHost(&p, bytes) != cudaSuccess) return nullptr;
+    return p;
+}
+
+int mg_host_free(void *p) { return cudaFreeHost(p) == cudaSuccess ? MG_OK : MG_ECUDA; }
+
+// ------------------------------------------------------------------ hot path
+int mg_vcycle_async(mg_ctx *ctx)
+{
+    CTX_OR_FAIL(ctx);
+    return ctx->vcycle();
+}
+
+int mg_vcycle(mg_ctx *ctx)
+{
+    CTX_OR_FAIL(ctx);
+    int rc = ctx->vcycle();
+    if (rc) return rc;
+    return ctx->sync();
+}
+
+int mg_synchronize(mg_ctx *ctx)
+{
+    CTX_OR_FAIL(ctx);
+    return ctx->sync();
+}
+
+int mg_step(mg_ctx *ctx, double *err)
+{
+    CTX_OR_FAIL(ctx);
+    return ctx->step(err);
+}
+
+int mg_run(mg_ctx *ctx, int max_cycles, double accuracy, double *errs, int *n_done)
+{
+    CTX_OR_FAIL(ctx);
+    int it = 0;
+    while (it < max_cycles) {
+        double err;
+        int rc = ctx->step(&err);
+        if (rc) return rc;
+        if (errs) errs[it] = err;
+        ++it;
+        if (err < accuracy || !std::isfinite(err)) break;  // cpu-raw.lua:256
+    }
+    if (n_done) *n_done = it;
+    return MG_OK;
+}
+
+int mg_step_host(mg_ctx *ctx, const void *f_host, void *psi_host, double *err)
+{
+    CTX_OR_FAIL(ctx);
+    if (!f_host || !psi_host) return ctx->fail(MG_EINVAL, "mg_step_host: null host pointer");
+    size_t nb = ctx->N * ctx->elem;
+    MG_CK(ctx, cudaMemcpyAsync(ctx->f, f_host, nb, cudaMemcpyHostToDevice, ctx->stream));
+    MG_CK(ctx, cudaMemcpyAsync(ctx->psi, psi_host, nb, cudaMemcpyHostToDevice, ctx->stream));
+    double e;
+    int rc = ctx->step(&e);
+    if (rc) return rc;
+    MG_CK(ctx, cudaMemcpyAsync(psi_host, ctx->psi, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if (err) *err = e;
+    return ctx->sync();
+}
+
+int mg_residual_norm(mg_ctx *ctx, double *rms)
+{
+    CTX_OR_FAIL(ctx);
+    if (!rms) return MG_EINVAL;
+    return ctx->eng->residual_norm(ctx, rms);
+}
+
+// ------------------------------------------------------------------ per-operator entry points
+static inline int lv_of(mg_ctx *ctx, int L)
+{
+    if (L < 1 || (L & (L - 1)) || L > ctx->size) return -1;
+    int k = 0;
+    while ((1 << k) < L) ++k;
+    return k;
+}
+
+int mg_twogrid(mg_ctx *ctx, double h, void *u, const void *f, int L)
+{
+    CTX_OR_FAIL(ctx);
+    int lv = lv_of(ctx, L);
+    if (lv < 0 || !u || !f) return ctx->fail(MG_EINVAL, "mg_twogrid: bad level or pointer");
+    if (ctx->mode == MG_MODE_REFSEQ && ctx->ensure_debug_arena() != MG_OK) return MG_ENOMEM;
+    int rc = ctx->mode == MG_MODE_REFSEQ ? ctx->eng->twogrid_refseq(ctx, h, u, f, lv)
+                                         : ctx->eng->twogrid_fused(ctx, h, u, f, lv);
+    if (rc) return rc;
+    return ctx->sync();
+}
+
+int mg_smooth(mg_ctx *ctx, int L, void *u, const void *f, double h, int n)
+{
+    CTX_OR_FAIL(ctx);
+    int lv = lv_of(ctx, L);
+    if (lv < 0 || !u || !f || n < 0) return ctx->fail(MG_EINVAL, "mg_smooth: bad argument");
+    int rc = ctx->eng->smooth(ctx, lv, u, f, h, n);
+    if (rc) return rc;
+    return ctx->sync();
+}
+
+int mg_jacobi(mg_ctx *ctx, int L, void *dest, const void *u, const void *f, double h)
+{
+    CTX_OR_FAIL(ctx);
+    if (lv_of(ctx, L) < 0 || !dest || !u || !f) return ctx->fail(MG_EINVAL, "mg_jacobi: bad argument");
+    int rc = ctx->eng->jacobi(ctx, L, dest, u, f, h);
+    if (rc) return rc;
+    return ctx->sync();
+}
+
+int mg_residual(mg_ctx *ctx, int L, void *r, const void *f, const void *u, double h)
+{
+    CTX_OR_FAIL(ctx);
+    if (lv_of(ctx, L) < 0 || !r || !u || !f) return ctx->fail(MG_EINVAL, "mg_residual: bad argument");
+    int rc = ctx->eng->residual(ctx, L, r, f, u, h);
+    if (rc) return rc;
+    return ctx->sync();
+}
+
+int mg_restrict(mg_ctx *ctx, int L2, void *R, const void *r)
+{
+    CTX_OR_FAIL(ctx);
+    if (lv_of(ctx, L2) < 0 || 2 * L2 > ctx->size || !R || !r)
+        return ctx->fail(MG_EINVAL, "mg_restrict: bad argument");
+    int rc = ctx->eng->restrict_(ctx, L2, R, r);
+    if (rc) return rc;
+    return ctx->sync();
+}
+
+int mg_prolong(mg_ctx *ctx, int L2, void *v, const void *V)
+{
+    CTX_OR_FAIL(ctx);
+    if (lv_of(ctx, L2) < 0 || 2 * L2 > ctx->size || !v || !V)
+        return ctx->fail(MG_EINVAL, "mg_prolong: bad argument");
+    int rc = ctx->eng->prolong(ctx, L2, v, V);
+    if (rc) return rc;
+    return ctx->sync();
+}
+
+int mg_add_to(mg_ctx *ctx, size_t n, void *u, const void *v)
+{
+    CTX_OR_FAIL(ctx);
+    if (!u || !v) return ctx->fail(MG_EINVAL, "mg_add_to: null pointer");
+    int rc = ctx->eng->add_to(ctx, n, u, v);
+    if (rc) return rc;
+    return ctx->sync();
+}
+
+int mg_frob_err(mg_ctx *ctx, double *err)
+{
+    CTX_OR_FAIL(ctx);
+    if (!err) return MG_EINVAL;
+    return ctx->eng->frob_err(ctx, err, ctx->mode == MG_MODE_REFSEQ);
+}
+
+int mg_smooth_residual_restrict(mg_ctx *ctx, int L, void *u, const void *f, double h, int n, void *R)
+{
+    CTX_OR_FAIL(ctx);
+    int lv = lv_of(ctx, L);
+    if (lv < 1 || !u || !f || !R || n < 0)
+        return ctx->fail(MG_EINVAL, "mg_smooth_residual_restrict: bad argument");
+    int rc = ctx->eng->pre_fused(ctx, lv, u, f, h, n, R);
+    if (rc) return rc;
+    return ctx->sync();
+}
+
+int mg_prolong_add_smooth(mg_ctx *ctx, int L, void *u, const void *f, double h, int n, const void *V)
+{
+    CTX_OR_FAIL(ctx);
+    int lv = lv_of(ctx, L);
+    if (lv < 1 || !u || !f || !V || n < 0)
+        return ctx->fail(MG_EINVAL, "mg_prolong_add_smooth: bad argument");
+    int rc = ctx->eng->post_fused(ctx, lv, u, f, h, n, V);
+    if (rc) return rc;
+    return ctx->sync();
+}
+
+// ------------------------------------------------------------------ trace
+int mg_trace_enable(mg_ctx *ctx, int on)
+{
+    if (!ctx) return MG_EINVAL;
+    ctx->trace_on = on != 0;
+    return MG_OK;
+}
+int mg_trace_clear(mg_ctx *ctx)
+{
+    if (!ctx) return MG_EINVAL;
+    ctx->trace.clear();
+    return MG_OK;
+}
+size_t mg_trace_count(mg_ctx *ctx) { return ctx ? ctx->trace.size() : 0; }
+int mg_trace_get(mg_ctx *ctx, size_t i, char *name, int *L, const void **host_data, size_t *bytes)
+{
+    if (!ctx || i >= ctx->trace.size()) return MG_EINVAL;
+    const TraceRec &r = ctx->trace[i];
+    if (name) *name = r.name;
+    if (L) *L = r.L;
+    if (host_data) *host_data = r.data.data();
+    if (bytes) *bytes = r.data.size();
+    return MG_OK;
+}
+
+// ------------------------------------------------------------------ measurement
+int mg_time_vcycles(mg_ctx *ctx, int n, float *ms_total)
+{
+    CTX_OR_FAIL(ctx);
+    if (n < 1 || !ms_total) return MG_EINVAL;
+    cudaEvent_t e0, e1;
+    MG_CK(ctx, cudaEventCreate(&e0));
+    MG_CK(ctx, cudaEventCreate(&e1));
+    MG_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    MG_CK(ctx, cudaEventRecord(e0, ctx->stream));
+    int rc = MG_OK;
+    for (int i = 0; i < n && rc == MG_OK; ++i) rc = ctx->vcycle();
+    MG_CK(ctx, cudaEventRecord(e1, ctx->stream));
+    MG_CK(ctx, cudaEventSynchronize(e1));
+    MG_CK(ctx, cudaEventElapsedTime(ms_total, e0, e1));
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return rc;
+}
+
+uint64_t mg_launch_count(mg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// One fused V-cycle, launched kernel by kernel (no graph) with a CUDA-event pair around every
+// launch. Fills up to `cap` records {kind, L, sweeps, ms}; *n = number of launches.
+int mg_profile_vcycle(mg_ctx *ctx, int cap, int *kind, int *L, int *sweeps, float *ms, int *n)
+{
+    CTX_OR_FAIL(ctx);
+    if (ctx->mode != MG_MODE_FUSED) return ctx->fail(MG_ESTATE, "mg_profile_vcycle: fused mode only");
+    ctx->prof.clear();
+    ctx->prof_on = true;
+    int rc = ctx->eng->twogrid_fused(ctx, 1.0 / ctx->size, ctx->psi, ctx->f, ctx->nlevels - 1);
+    ctx->prof_on = false;
+    cudaError_t e = cudaStreamSynchronize(ctx->stream);
+    int cnt = 0;
+    for (auto &r : ctx->prof) {
+        if (e == cudaSuccess) cudaEventElapsedTime(&r.ms, r.e0, r.e1);
+        if (cnt < cap) {
+            if (kind) kind[cnt] = r.kind;
+            if (L) L[cnt] = r.L;
+            if (sweeps) sweeps[cnt] = r.sweeps;
+            if (ms) ms[cnt] = r.ms;
+        }
+        ++cnt;
+        cudaEventDestroy(r.e0);
+        cudaEventDestroy(r.e1);
+    }
+    ctx->prof.clear();
+    if (n) *n = cnt;
+    if (rc) return rc;
+    if (e != cudaSuccess) return ctx->fail_cuda(e, "mg_profile_vcycle");
+    return MG_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU slabs
+int mg_create_slab(int dim, int size, int real_kind, int smooth, int device, int rank, int nranks,
+                   mg_ctx **out)
+{
+    if (nranks == 1 && rank == 0) return create_common(dim, size, real_kind, smooth, device, 0, 1, out);
+    g_create_error = "mg_create_slab: slab decomposition not implemented yet";
+    if (out) *out = nullptr;
+    return MG_EUNSUPPORTED;
+}
+int mg_slab_ipc_size(void) { return (int)sizeof(cudaIpcMemHandle_t); }
+int mg_slab_export(mg_ctx *ctx, void *, size_t) { return ctx ? ctx->fail(MG_EUNSUPPORTED, "slabs: not implemented") : MG_EINVAL; }
+int mg_slab_attach(mg_ctx *ctx, int, const void *, size_t) { return ctx ? ctx->fail(MG_EUNSUPPORTED, "slabs: not implemented") : MG_EINVAL; }
+int mg_slab_attach_local(mg_ctx *ctx, int, mg_ctx *) { return ctx ? ctx->fail(MG_EUNSUPPORTED, "slabs: not implemented") : MG_EINVAL; }
+
+}  // extern "C"

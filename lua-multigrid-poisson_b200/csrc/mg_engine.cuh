@@ -1,0 +1,635 @@
+// mg_engine.cuh -- context (grid-hierarchy arena, streams, graph) and the typed engine that
+// schedules kernels for one (storage type, arithmetic type, dimension) combination.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/mgpoisson.h"
+#include "mg_fused_simple.cuh"
+#include "mg_math.cuh"
+#include "mg_ops_ref.cuh"
+#include "mg_small.cuh"
+
+namespace mg {
+
+constexpr int MAX_LEVELS = 24;
+constexpr size_t ARENA_ALIGN = 1024;
+
+struct TraceRec {
+    char name;
+    int L;
+    std::vector<unsigned char> data;
+};
+
+// one record per kernel launch of a profiled (ungraphed) V-cycle
+struct ProfRec {
+    int kind;    // MG_K_* below
+    int L;       // level width
+    int sweeps;  // Jacobi sweeps performed by the launch
+    cudaEvent_t e0, e1;
+    float ms;
+};
+enum { MG_K_SWEEP = 0, MG_K_RESID_RESTRICT = 1, MG_K_SMALL = 2, MG_K_PROLONG_ADD = 3, MG_K_COPY = 4,
+       MG_K_SWEEP_PROLONG = 5, MG_K_SWEEP_RESTRICT = 6 };
+
+struct Engine;
+
+}  // namespace mg
+
+#define MG_CK(ctx, call)                                             \
+    do {                                                             \
+        cudaError_t e_ = (call);                                     \
+        if (e_ != cudaSuccess) return (ctx)->fail_cuda(e_, #call);   \
+    } while (0)
+
+struct mg_ctx {
+    int dim = 0, size = 0, real_kind = 0, smooth = 7, device = 0, nlevels = 0, rank = 0, nranks = 1;
+    size_t elem = 0, N = 0;
+    int mode = MG_MODE_FUSED, tb = 1, small_L = 0, use_graph = 1;
+
+    // ---- grid-hierarchy arena (K-f): one allocation, zero-filled once (cpu-raw.lua:159-171)
+    void *arena = nullptr;
+    size_t arena_bytes = 0;
+    void *f = nullptr, *psi = nullptr, *psiOld = nullptr;
+    void *R[mg::MAX_LEVELS] = {}, *V[mg::MAX_LEVELS] = {}, *W[mg::MAX_LEVELS] = {};
+    // buffers only the reference sequence / debug dumps need; allocated on first use
+    void *debug_arena = nullptr;
+    size_t debug_arena_bytes = 0;
+    void *errorBuf = nullptr, *tmpU = nullptr;
+    void *r[mg::MAX_LEVELS] = {}, *v[mg::MAX_LEVELS] = {};
+
+    // ---- reductions
+    double *d_partial = nullptr, *d_scalar = nullptr, *h_scalar = nullptr;
+    int npartial = 0;
+
+    // ---- streams / graph
+    cudaStream_t own_stream = nullptr, stream = nullptr, cap_stream = nullptr;
+    bool borrowed_stream = false, capturing = false;
+    cudaGraph_t graph = nullptr;
+    cudaGraphExec_t gexec = nullptr;
+    size_t graph_nodes = 0;
+    uint64_t launches = 0;
+
+    bool prof_on = false;
+    std::vector<mg::ProfRec> prof;
+
+    std::string err;
+    bool trace_on = false;
+    std::vector<mg::TraceRec> trace;
+    mg::Engine *eng = nullptr;
+
+    size_t level_elems(int lv) const
+    {
+        size_t L = (size_t)1 << lv;
+        return L * L * (dim == 3 ? L : 1);
+    }
+    size_t level_bytes(int lv) const { return level_elems(lv) * elem; }
+
+    int fail(int code, const char *msg)
+    {
+        err = msg;
+        return code;
+    }
+    int fail_cuda(cudaError_t e, const char *what)
+    {
+        err = std::string(what) + ": " + cudaGetErrorString(e);
+        return MG_ECUDA;
+    }
+    int activate()
+    {
+        int cur = -1;
+        if (cudaGetDevice(&cur) != cudaSuccess || cur != device) MG_CK(this, cudaSetDevice(device));
+        return MG_OK;
+    }
+    int sync()
+    {
+        MG_CK(this, cudaStreamSynchronize(stream));
+        return MG_OK;
+    }
+    void count_launch(int n = 1)
+    {
+        if (!capturing) launches += (uint64_t)n;
+    }
+    // bracket one launch with events when profiling (never while capturing a graph)
+    void prof_begin(int kind, int L, int sweeps)
+    {
+        if (!prof_on || capturing) return;
+        mg::ProfRec r{kind, L, sweeps, nullptr, nullptr, 0.f};
+        cudaEventCreate(&r.e0);
+        cudaEventCreate(&r.e1);
+        cudaEventRecord(r.e0, stream);
+        prof.push_back(r);
+    }
+    void prof_end()
+    {
+        if (!prof_on || capturing || prof.empty()) return;
+        cudaEventRecord(prof.back().e1, stream);
+    }
+
+    int init(int dim_, int size_, int real_kind_, int smooth_, int device_, int rank_, int nranks_);
+    void release();
+    int ensure_debug_arena();
+    void *buffer(int which, int level, size_t *cap);
+    void drop_graph();
+    int vcycle();
+    int step(double *err_out);
+    int trace_rec(char name, int L, const void *dev, size_t bytes);
+};
+
+namespace mg {
+
+struct Engine {
+    virtual ~Engine() {}
+    virtual int init_cells(mg_ctx *c) = 0;
+    virtual int jacobi(mg_ctx *c, int L, void *dest, const void *u, const void *f, double h) = 0;
+    virtual int residual(mg_ctx *c, int L, void *r, const void *f, const void *u, double h) = 0;
+    virtual int restrict_(mg_ctx *c, int L2, void *R, const void *r) = 0;
+    virtual int prolong(mg_ctx *c, int L2, void *v, const void *V) = 0;
+    virtual int add_to(mg_ctx *c, size_t n, void *u, const void *v) = 0;
+    virtual int smooth(mg_ctx *c, int lv, void *u, const void *f, double h, int n) = 0;
+    virtual int pre_fused(mg_ctx *c, int lv, void *u, const void *f, double h, int n, void *R) = 0;
+    virtual int post_fused(mg_ctx *c, int lv, void *u, const void *f, double h, int n, const void *V) = 0;
+    virtual int twogrid_refseq(mg_ctx *c, double h, void *u, const void *f, int lv) = 0;
+    virtual int twogrid_fused(mg_ctx *c, double h, void *u, const void *f, int lv) = 0;
+    virtual int frob_err(mg_ctx *c, double *err, bool materialise) = 0;
+    virtual int residual_norm(mg_ctx *c, double *rms) = 0;
+};
+
+static inline dim3 grid_for(int dim, int L, dim3 b)
+{
+    return dim3((unsigned)((L + b.x - 1) / b.x), (unsigned)((L + b.y - 1) / b.y), dim == 3 ? (unsigned)L : 1u);
+}
+static inline dim3 block_for(int L)
+{
+    if (L >= 128) return dim3(128, 2, 1);
+    if (L >= 32) return dim3(32, 8, 1);
+    return dim3(8, 8, 1);
+}
+
+#define MG_LAUNCH_CHECK(c)                                   \
+    do {                                                     \
+        cudaError_t e_ = cudaGetLastError();                 \
+        if (e_ != cudaSuccess) return (c)->fail_cuda(e_, "kernel launch"); \
+        (c)->count_launch();                                 \
+    } while (0)
+
+template <typename R, typename A, int DIM> struct EngineT : Engine {
+    // ------------------------------------------------------------ reference operators
+    int init_cells(mg_ctx *c) override
+    {
+        dim3 b = block_for(c->size), g = grid_for(DIM, c->size, b);
+        k_init_cells<R, A, DIM><<<g, b, 0, c->stream>>>((R *)c->f, (R *)c->psi, c->size);
+        MG_LAUNCH_CHECK(c);
+        return MG_OK;
+    }
+    int jacobi(mg_ctx *c, int L, void *dest, const void *u, const void *f, double h) override
+    {
+        dim3 b = block_for(L), g = grid_for(DIM, L, b);
+        k_jacobi<R, A, DIM><<<g, b, 0, c->stream>>>((R *)dest, (const R *)u, (const R *)f, L,
+                                                    make_coef<A>(DIM, h));
+        MG_LAUNCH_CHECK(c);
+        return MG_OK;
+    }
+    int residual(mg_ctx *c, int L, void *r, const void *f, const void *u, double h) override
+    {
+        dim3 b = block_for(L), g = grid_for(DIM, L, b);
+        k_residual<R, A, DIM><<<g, b, 0, c->stream>>>((R *)r, (const R *)f, (const R *)u, L,
+                                                      make_coef<A>(DIM, h));
+        MG_LAUNCH_CHECK(c);
+        return MG_OK;
+    }
+    int restrict_(mg_ctx *c, int L2, void *Rc, const void *r) override
+    {
+        dim3 b = block_for(L2), g = grid_for(DIM, L2, b);
+        k_restrict<R, A, DIM><<<g, b, 0, c->stream>>>((R *)Rc, (const R *)r, L2);
+        MG_LAUNCH_CHECK(c);
+        return MG_OK;
+    }
+    int prolong(mg_ctx *c, int L2, void *v, const void *V) override
+    {
+        int L = 2 * L2;
+        dim3 b = block_for(L), g = grid_for(DIM, L, b);
+        k_prolong<R, DIM><<<g, b, 0, c->stream>>>((R *)v, (const R *)V, L);
+        MG_LAUNCH_CHECK(c);
+        return MG_OK;
+    }
+    int add_to(mg_ctx *c, size_t n, void *u, const void *v) override
+    {
+        unsigned nb = (unsigned)((n + 255) / 256);
+        k_add_to<R, A><<<nb, 256, 0, c->stream>>>((R *)u, (const R *)v, n);
+        MG_LAUNCH_CHECK(c);
+        return MG_OK;
+    }
+
+    // cpu-raw.lua:176-184 inPlaceIterativeSolver, literally: Jacobi into tmpU, copy back
+    int in_place_solver(mg_ctx *c, int lv, R *u, const R *f, double h)
+    {
+        int rc = jacobi(c, 1 << lv, c->tmpU, u, f, h);
+        if (rc) return rc;
+        MG_CK(c, cudaMemcpyAsync(u, c->tmpU, c->level_bytes(lv), cudaMemcpyDeviceToDevice, c->stream));
+        return MG_OK;
+    }
+
+    // cpu-raw.lua:186-237 twoGrid, one launch per reference operator, trace at the show sites
+    int twogrid_refseq(mg_ctx *c, double h, void *u_, const void *f_, int lv) override
+    {
+        R *u = (R *)u_;
+        const R *f = (const R *)f_;
+        const int L = 1 << lv;
+        const size_t nb = c->level_bytes(lv);
+        int rc;
+        if (L == 1) {
+            if ((rc = c->trace_rec('f', L, f, nb))) return rc;
+            if ((rc = in_place_solver(c, lv, u, f, h))) return rc;
+            return c->trace_rec('u', L, u, nb);
+        }
+        for (int i = 1; i <= c->smooth; ++i) {
+            if (L == c->size && (rc = c->trace_rec('f', L, f, nb))) return rc;
+            if ((rc = in_place_solver(c, lv, u, f, h))) return rc;
+            if ((rc = c->trace_rec('u', L, u, nb))) return rc;
+        }
+        R *r = (R *)c->r[lv];
+        if ((rc = c->trace_rec('f', L, f, nb))) return rc;
+        if ((rc = c->trace_rec('u', L, u, nb))) return rc;
+        if ((rc = residual(c, L, r, f, u, h))) return rc;
+        if ((rc = c->trace_rec('r', L, r, nb))) return rc;
+        const int L2 = L / 2;
+        const size_t nb2 = c->level_bytes(lv - 1);
+        R *Rc = (R *)c->R[lv - 1];
+        if ((rc = restrict_(c, L2, Rc, r))) return rc;
+        if ((rc = c->trace_rec('R', L2, Rc, nb2))) return rc;
+        R *Vc = (R *)c->V[lv - 1];
+        if ((rc = twogrid_refseq(c, 2 * h, Vc, Rc, lv - 1))) return rc;
+        if ((rc = c->trace_rec('V', L2, Vc, nb2))) return rc;
+        R *v = (R *)c->v[lv];
+        if ((rc = prolong(c, L2, v, Vc))) return rc;
+        if ((rc = c->trace_rec('v', L, v, nb))) return rc;
+        if ((rc = add_to(c, c->level_elems(lv), u, v))) return rc;
+        if ((rc = c->trace_rec('u', L, u, nb))) return rc;
+        for (int i = 1; i <= c->smooth; ++i) {
+            if ((rc = in_place_solver(c, lv, u, f, h))) return rc;
+            if ((rc = c->trace_rec('u', L, u, nb))) return rc;
+        }
+        return MG_OK;
+    }
+
+    // ------------------------------------------------------------ fused passes
+    // n sweeps starting from `cur` (ping-pong with `oth`), the first optionally reading
+    // cur + prolong(Vp), followed optionally by Rout = restrict(f - A cur).
+    int sweeps(mg_ctx *c, int lv, R *&cur, R *&oth, const R *f, double h, int n, const R *Vp, R *Rout)
+    {
+        const int L = 1 << lv;
+        const Coef<A> cf = make_coef<A>(DIM, h);
+        dim3 b = block_for(L), g = grid_for(DIM, L, b);
+        for (int s = 0; s < n; ++s) {
+            c->prof_begin(s == 0 && Vp ? MG_K_SWEEP_PROLONG : MG_K_SWEEP, L, 1);
+            if (s == 0 && Vp)
+                k_sweep_pp<R, A, DIM, true><<<g, b, 0, c->stream>>>(oth, cur, f, Vp, L, cf);
+            else
+                k_sweep_pp<R, A, DIM, false><<<g, b, 0, c->stream>>>(oth, cur, f, nullptr, L, cf);
+            c->prof_end();
+            MG_LAUNCH_CHECK(c);
+            R *t = cur; cur = oth; oth = t;
+        }
+        if (n == 0 && Vp) {
+            c->prof_begin(MG_K_PROLONG_ADD, L, 0);
+            k_prolong_add<R, A, DIM><<<g, b, 0, c->stream>>>(cur, Vp, L);
+            c->prof_end();
+            MG_LAUNCH_CHECK(c);
+        }
+        if (Rout) {
+            const int L2 = L / 2;
+            dim3 b2 = block_for(L2), g2 = grid_for(DIM, L2, b2);
+            c->prof_begin(MG_K_RESID_RESTRICT, L, 0);
+            k_residual_restrict<R, A, DIM><<<g2, b2, 0, c->stream>>>(Rout, f, cur, L, cf);
+            c->prof_end();
+            MG_LAUNCH_CHECK(c);
+        }
+        return MG_OK;
+    }
+    int settle(mg_ctx *c, int lv, R *u, R *cur)
+    {
+        if (cur != u) {
+            c->prof_begin(MG_K_COPY, 1 << lv, 0);
+            MG_CK(c, cudaMemcpyAsync(u, cur, c->level_bytes(lv), cudaMemcpyDeviceToDevice, c->stream));
+            c->prof_end();
+        }
+        return MG_OK;
+    }
+    int smooth(mg_ctx *c, int lv, void *u_, const void *f, double h, int n) override
+    {
+        R *u = (R *)u_;
+        if (c->mode == MG_MODE_REFSEQ) {
+            int rc = c->ensure_debug_arena();
+            for (int i = 0; i < n && !rc; ++i) rc = in_place_solver(c, lv, u, (const R *)f, h);
+            return rc;
+        }
+        R *cur = u, *oth = (R *)c->W[lv];
+        int rc = sweeps(c, lv, cur, oth, (const R *)f, h, n, nullptr, nullptr);
+        if (rc) return rc;
+        return settle(c, lv, u, cur);
+    }
+    int pre_fused(mg_ctx *c, int lv, void *u_, const void *f, double h, int n, void *Rout) override
+    {
+        R *u = (R *)u_, *cur = u, *oth = (R *)c->W[lv];
+        int rc = sweeps(c, lv, cur, oth, (const R *)f, h, n, nullptr, (R *)Rout);
+        if (rc) return rc;
+        return settle(c, lv, u, cur);
+    }
+    int post_fused(mg_ctx *c, int lv, void *u_, const void *f, double h, int n, const void *Vp) override
+    {
+        R *u = (R *)u_, *cur = u, *oth = (R *)c->W[lv];
+        int rc = sweeps(c, lv, cur, oth, (const R *)f, h, n, (const R *)Vp, nullptr);
+        if (rc) return rc;
+        return settle(c, lv, u, cur);
+    }
+
+    // (K-d) every level <= lv in one launch of the persistent kernel
+    int small_vcycle(mg_ctx *c, double h, R *u, const R *f, int lv)
+    {
+        SmallArgs<R, A> a;
+        memset(&a, 0, sizeof(a));
+        a.top = lv;
+        a.smooth = c->smooth;
+        double hl = h;
+        for (int l = lv; l >= 0; --l, hl *= 2) {
+            a.u[l] = l == lv ? u : (R *)c->V[l];
+            a.f[l] = l == lv ? f : (const R *)c->R[l];
+            a.w[l] = (R *)c->W[l];
+            a.coef[l] = make_coef<A>(DIM, hl);
+        }
+        size_t n = c->level_elems(lv);
+        int threads = n >= 1024 ? 1024 : (n >= 256 ? 256 : 64);
+        c->prof_begin(MG_K_SMALL, 1 << lv, 2 * c->smooth);
+        k_small_vcycle<R, A, DIM><<<1, threads, 0, c->stream>>>(a);
+        c->prof_end();
+        MG_LAUNCH_CHECK(c);
+        return MG_OK;
+    }
+
+    int twogrid_fused(mg_ctx *c, double h, void *u_, const void *f_, int lv) override
+    {
+        R *u = (R *)u_;
+        const R *f = (const R *)f_;
+        if (lv == 0 || (1 << lv) <= c->small_L) return small_vcycle(c, h, u, f, lv);
+        R *cur = u, *oth = (R *)c->W[lv];
+        R *Rc = (R *)c->R[lv - 1], *Vc = (R *)c->V[lv - 1];
+        int rc;
+        if ((rc = sweeps(c, lv, cur, oth, f, h, c->smooth, nullptr, Rc))) return rc;
+        if ((rc = twogrid_fused(c, 2 * h, Vc, Rc, lv - 1))) return rc;
+        if ((rc = sweeps(c, lv, cur, oth, f, h, c->smooth, Vc, nullptr))) return rc;
+        return settle(c, lv, u, cur);
+    }
+
+    // ------------------------------------------------------------ norms
+    int reduce_to_host(mg_ctx *c, double *out)
+    {
+        k_final_sum<<<1, 1024, 0, c->stream>>>(c->d_partial, c->npartial, c->d_scalar);
+        MG_LAUNCH_CHECK(c);
+        MG_CK(c, cudaMemcpyAsync(c->h_scalar, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        MG_CK(c, cudaStreamSynchronize(c->stream));
+        *out = *c->h_scalar;
+        return MG_OK;
+    }
+    // cpu-raw.lua:249-254
+    int frob_err(mg_ctx *c, double *err, bool materialise) override
+    {
+        if (materialise) {
+            int rc = c->ensure_debug_arena();
+            if (rc) return rc;
+        }
+        k_frob_partial<R, A><<<c->npartial, 256, 0, c->stream>>>(
+            (const R *)c->psi, (const R *)c->psiOld, materialise ? (R *)c->errorBuf : nullptr, c->N,
+            c->d_partial);
+        MG_LAUNCH_CHECK(c);
+        double s;
+        int rc = reduce_to_host(c, &s);
+        if (rc) return rc;
+        *err = std::sqrt(s / (double)c->N);
+        return MG_OK;
+    }
+    int residual_norm(mg_ctx *c, double *rms) override
+    {
+        // uses the partner of psi as scratch for r; W[top] is free outside a V-cycle
+        const int top = c->nlevels - 1;
+        R *scratch = (R *)c->W[top];
+        int rc = residual(c, c->size, scratch, c->f, c->psi, 1.0 / c->size);
+        if (rc) return rc;
+        k_sumsq_partial<R><<<c->npartial, 256, 0, c->stream>>>(scratch, c->N, c->d_partial);
+        MG_LAUNCH_CHECK(c);
+        double s;
+        if ((rc = reduce_to_host(c, &s))) return rc;
+        *rms = std::sqrt(s / (double)c->N);
+        return MG_OK;
+    }
+};
+
+}  // namespace mg
+
+// ======================================================================= mg_ctx methods
+inline int mg_ctx::init(int dim_, int size_, int real_kind_, int smooth_, int device_, int rank_, int nranks_)
+{
+    dim = dim_; size = size_; real_kind = real_kind_; rank = rank_; nranks = nranks_;
+    smooth = smooth_ > 0 ? smooth_ : 7;  // cpu-raw.lua:123
+    elem = real_kind == MG_REAL_F64 ? 8 : 4;
+    nlevels = 0;
+    while ((1 << nlevels) < size) ++nlevels;
+    ++nlevels;
+    if (nlevels > mg::MAX_LEVELS) return fail(MG_EINVAL, "too many levels");
+    N = level_elems(nlevels - 1);
+    small_L = dim == 3 ? 16 : 64;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(MG_ECUDA, "no CUDA device: libmgpoisson has no CPU fallback");
+    if (device_ < 0) MG_CK(this, cudaGetDevice(&device_));
+    device = device_;
+    MG_CK(this, cudaSetDevice(device));
+    MG_CK(this, cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
+    MG_CK(this, cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
+    stream = own_stream;
+
+    // arena layout: f, psi, psiOld, then per level R, V (below the top) and the ping-pong partner W
+    auto up = [](size_t x) { return (x + mg::ARENA_ALIGN - 1) / mg::ARENA_ALIGN * mg::ARENA_ALIGN; };
+    const int top = nlevels - 1;
+    size_t off = 0;
+    size_t o_f = off; off += up(N * elem);
+    size_t o_psi = off; off += up(N * elem);
+    size_t o_old = off; off += up(N * elem);
+    size_t o_R[mg::MAX_LEVELS], o_V[mg::MAX_LEVELS], o_W[mg::MAX_LEVELS];
+    for (int lv = 0; lv <= top; ++lv) {
+        if (lv < top) {
+            o_R[lv] = off; off += up(level_bytes(lv));
+            o_V[lv] = off; off += up(level_bytes(lv));
+        }
+        o_W[lv] = off; off += up(level_bytes(lv));
+    }
+    arena_bytes = off;
+    e = cudaMalloc(&arena, arena_bytes);
+    if (e != cudaSuccess) {
+        arena = nullptr;
+        cudaGetLastError();
+        return fail(MG_ENOMEM, "cudaMalloc of the grid-hierarchy arena failed");
+    }
+    MG_CK(this, cudaMemsetAsync(arena, 0, arena_bytes, stream));
+    char *base = (char *)arena;
+    f = base + o_f; psi = base + o_psi; psiOld = base + o_old;
+    for (int lv = 0; lv <= top; ++lv) {
+        if (lv < top) { R[lv] = base + o_R[lv]; V[lv] = base + o_V[lv]; }
+        W[lv] = base + o_W[lv];
+    }
+    npartial = 1184;  // 8 blocks per SM on 148 SMs
+    MG_CK(this, cudaMalloc(&d_partial, sizeof(double) * (size_t)(npartial + 8)));
+    d_scalar = d_partial + npartial;
+    MG_CK(this, cudaMallocHost(&h_scalar, sizeof(double) * 8));
+
+    switch (real_kind * 10 + dim) {
+    case MG_REAL_F64 * 10 + 2: eng = new mg::EngineT<double, double, 2>(); break;
+    case MG_REAL_F64 * 10 + 3: eng = new mg::EngineT<double, double, 3>(); break;
+    case MG_REAL_F32 * 10 + 2: eng = new mg::EngineT<float, float, 2>(); break;
+    case MG_REAL_F32 * 10 + 3: eng = new mg::EngineT<float, float, 3>(); break;
+    case MG_REAL_F32_ACC64 * 10 + 2: eng = new mg::EngineT<float, double, 2>(); break;
+    case MG_REAL_F32_ACC64 * 10 + 3: eng = new mg::EngineT<float, double, 3>(); break;
+    default: return fail(MG_EINVAL, "bad real_kind/dim");
+    }
+    int rc = eng->init_cells(this);  // cpu-raw.lua:173
+    if (rc) return rc;
+    return sync();
+}
+
+inline void mg_ctx::release()
+{
+    if (device >= 0) cudaSetDevice(device);
+    drop_graph();
+    if (own_stream) cudaStreamSynchronize(own_stream);
+    if (arena) cudaFree(arena);
+    if (debug_arena) cudaFree(debug_arena);
+    if (d_partial) cudaFree(d_partial);
+    if (h_scalar) cudaFreeHost(h_scalar);
+    if (own_stream) cudaStreamDestroy(own_stream);
+    if (cap_stream) cudaStreamDestroy(cap_stream);
+    delete eng;
+    arena = debug_arena = nullptr; d_partial = nullptr; h_scalar = nullptr;
+    own_stream = cap_stream = nullptr; eng = nullptr;
+}
+
+inline int mg_ctx::ensure_debug_arena()
+{
+    if (debug_arena) return MG_OK;
+    auto up = [](size_t x) { return (x + mg::ARENA_ALIGN - 1) / mg::ARENA_ALIGN * mg::ARENA_ALIGN; };
+    const int top = nlevels - 1;
+    size_t off = 0;
+    size_t o_err = off; off += up(N * elem);
+    size_t o_tmp = off; off += up(N * elem);
+    size_t o_Rt = off; off += up(N * elem);
+    size_t o_Vt = off; off += up(N * elem);
+    size_t o_r[mg::MAX_LEVELS], o_v[mg::MAX_LEVELS];
+    for (int lv = 0; lv <= top; ++lv) {
+        o_r[lv] = off; off += up(level_bytes(lv));
+        o_v[lv] = off; off += up(level_bytes(lv));
+    }
+    cudaError_t e = cudaMalloc(&debug_arena, off);
+    if (e != cudaSuccess) {
+        debug_arena = nullptr;
+        cudaGetLastError();
+        return fail(MG_ENOMEM, "cudaMalloc of the reference-sequence arena failed");
+    }
+    debug_arena_bytes = off;
+    MG_CK(this, cudaMemsetAsync(debug_arena, 0, off, stream));
+    char *base = (char *)debug_arena;
+    errorBuf = base + o_err; tmpU = base + o_tmp;
+    R[top] = base + o_Rt; V[top] = base + o_Vt;  // allocated by the reference, never used (cpu-raw.lua:162,164)
+    for (int lv = 0; lv <= top; ++lv) { r[lv] = base + o_r[lv]; v[lv] = base + o_v[lv]; }
+    return MG_OK;
+}
+
+inline void *mg_ctx::buffer(int which, int level, size_t *cap)
+{
+    int lv = nlevels - 1;
+    if (which >= MG_BUF_r) {
+        if (level < 1 || (level & (level - 1)) || level > size) return nullptr;
+        lv = 0;
+        while ((1 << lv) < level) ++lv;
+    }
+    if (cap) *cap = level_bytes(lv);
+    switch (which) {
+    case MG_BUF_F: return f;
+    case MG_BUF_PSI: return psi;
+    case MG_BUF_PSIOLD: return psiOld;
+    case MG_BUF_ERRORBUF: return errorBuf;
+    case MG_BUF_TMPU: return tmpU;
+    case MG_BUF_r: return r[lv];
+    case MG_BUF_R: return R[lv];
+    case MG_BUF_v: return v[lv];
+    case MG_BUF_V: return V[lv];
+    }
+    return nullptr;
+}
+
+inline void mg_ctx::drop_graph()
+{
+    if (gexec) cudaGraphExecDestroy(gexec);
+    if (graph) cudaGraphDestroy(graph);
+    gexec = nullptr; graph = nullptr; graph_nodes = 0;
+}
+
+// twoGrid(1/size, psi, f, size) (cpu-raw.lua:247)
+inline int mg_ctx::vcycle()
+{
+    const double h = 1.0 / size;  // cpu-raw.lua:242
+    const int top = nlevels - 1;
+    if (mode == MG_MODE_REFSEQ) {
+        int rc = ensure_debug_arena();
+        if (rc) return rc;
+        return eng->twogrid_refseq(this, h, psi, f, top);
+    }
+    if (!use_graph) return eng->twogrid_fused(this, h, psi, f, top);
+    if (!gexec) {
+        cudaStream_t saved = stream;
+        MG_CK(this, cudaStreamSynchronize(saved));
+        MG_CK(this, cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
+        stream = cap_stream; capturing = true;
+        int rc = eng->twogrid_fused(this, h, psi, f, top);
+        stream = saved; capturing = false;
+        cudaError_t e = cudaStreamEndCapture(cap_stream, &graph);
+        if (rc) { if (graph) cudaGraphDestroy(graph); graph = nullptr; return rc; }
+        if (e != cudaSuccess) { graph = nullptr; return fail_cuda(e, "cudaStreamEndCapture"); }
+        MG_CK(this, cudaGraphInstantiate(&gexec, graph, 0));
+        size_t nn = 0;
+        MG_CK(this, cudaGraphGetNodes(graph, nullptr, &nn));
+        graph_nodes = nn;
+    }
+    MG_CK(this, cudaGraphLaunch(gexec, stream));
+    launches += graph_nodes;
+    return MG_OK;
+}
+
+// loop body of run() (cpu-raw.lua:246-254)
+inline int mg_ctx::step(double *err_out)
+{
+    MG_CK(this, cudaMemcpyAsync(psiOld, psi, N * elem, cudaMemcpyDeviceToDevice, stream));
+    int rc = vcycle();
+    if (rc) return rc;
+    double e;
+    rc = eng->frob_err(this, &e, mode == MG_MODE_REFSEQ);
+    if (rc) return rc;
+    if (err_out) *err_out = e;
+    return MG_OK;
+}
+
+inline int mg_ctx::trace_rec(char name, int L, const void *dev, size_t bytes)
+{
+    if (!trace_on) return MG_OK;
+    mg::TraceRec rec;
+    rec.name = name; rec.L = L;
+    rec.data.resize(bytes);
+    MG_CK(this, cudaMemcpyAsync(rec.data.data(), dev, bytes, cudaMemcpyDeviceToHost, stream));
+    MG_CK(this, cudaStreamSynchronize(stream));
+    trace.push_back(std::move(rec));
+    return MG_OK;
+}

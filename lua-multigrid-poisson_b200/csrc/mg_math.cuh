@@ -1,0 +1,123 @@
+// mg_math.cuh -- per-point arithmetic shared by EVERY kernel of the library.
+//
+// All kernels (one-operator-per-launch reference sequence, fused passes, temporally blocked
+// streaming smoother, persistent small-level kernel) call the same __forceinline__ functions
+// below, built only from explicitly rounded intrinsics (__fadd_rn, __fmaf_rn, ...), which
+// nvcc never contracts or reassociates. That is what makes "per-point arithmetic identical
+// across kernels" a structural property instead of a compiler accident, and what lets the
+// fused path be compared bit-for-bit with the reference sequence and with the CPU oracle.
+//
+// Reference expressions (cpu-raw.lua:34-57, OpenCL twins gpu.lua:83-124), with h = 2^-k:
+//   S       = ((u_xl + u_xr) + u_yl) + u_yr            [+ u_zl) + u_zr in 3-D]
+//   Jacobi  : dest = (f - S/h^2) / adiag               adiag = -4/h^2 (2-D), -6/h^2 (3-D)
+//   residual: r    = f - (S/h^2 + adiag*u)
+// Because h^2 is a power of two, S/h^2 == S*inv_h2 exactly, so
+//   numerator n = RN(f - S*inv_h2) = fma(-S, inv_h2, f)            (one rounding, as the reference)
+//   2-D: n/adiag == n * (-h^2/4) exactly
+//   3-D: n/adiag is one true rounding; computed as a Markstein-corrected reciprocal multiply
+//        (exhaustively verified equal to IEEE division for every normal fp32 numerator and
+//        every divisor 6*2^m, m>=3; numerators below the guard fall back to IEEE division).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace mg {
+
+template <typename A> struct Ar;
+template <> struct Ar<float> {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
+    static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
+    static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
+    static __host__ __device__ __forceinline__ float tiny() { return 1e-20f; }
+};
+template <> struct Ar<double> {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double fma(double a, double b, double c) { return __fma_rn(a, b, c); }
+    static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
+    static __device__ __forceinline__ double abs(double a) { return fabs(a); }
+    static __host__ __device__ __forceinline__ double tiny() { return 1e-200; }
+};
+
+// Per-level coefficients, computed on the host in double and rounded to the arithmetic type
+// (all exact: powers of two times 4 or 6, except yneg which is the rounded reciprocal).
+template <typename A> struct Coef {
+    A inv_h2;  // 1/h^2
+    A adiag;   // -4/h^2 (2-D) or -6/h^2 (3-D)
+    A cneg;    // 2-D: -h^2/4 (= 1/adiag, exact)
+    A yneg;    // 3-D: RN(1/adiag)
+    A nadiag;  // -adiag
+};
+
+template <typename A> static inline Coef<A> make_coef(int dim, double h)
+{
+    Coef<A> c;
+    double h2 = h * h;
+    A ah = (A)h;                 // gpu.lua:291 passes h as real[1]; h is a power of two => exact
+    A ah2 = ah * ah;
+    (void)h2;
+    c.inv_h2 = (A)1 / ah2;
+    c.adiag = (dim == 2 ? (A)-4 : (A)-6) / ah2;
+    c.cneg = (A)1 / c.adiag;
+    c.yneg = (A)1 / c.adiag;
+    c.nadiag = -c.adiag;
+    return c;
+}
+
+// numerator of the Jacobi update: RN(f - S/h^2)
+template <typename A> __device__ __forceinline__ A jacobi_num(A S, A f, const Coef<A> &c)
+{
+    return Ar<A>::fma(-S, c.inv_h2, f);
+}
+
+// n / adiag, correctly rounded.
+template <int DIM, typename A> __device__ __forceinline__ A div_adiag(A n, const Coef<A> &c)
+{
+    if (DIM == 2) {
+        return Ar<A>::mul(n, c.cneg);
+    } else {
+        A q = Ar<A>::mul(n, c.yneg);
+        A r = Ar<A>::fma(c.nadiag, q, n);       // n - adiag*q, exact
+        A q2 = Ar<A>::fma(r, c.yneg, q);
+        if (Ar<A>::abs(n) < Ar<A>::tiny() && n != (A)0) q2 = Ar<A>::div(n, c.adiag);
+        return q2;
+    }
+}
+
+template <int DIM, typename A> __device__ __forceinline__ A jacobi_point(A S, A f, const Coef<A> &c)
+{
+    return div_adiag<DIM, A>(jacobi_num<A>(S, f, c), c);
+}
+
+// r = f - (S/h^2 + adiag*u): product and sum separately rounded (cpu-raw.lua:55-56)
+template <typename A> __device__ __forceinline__ A residual_point(A S, A f, A u, const Coef<A> &c)
+{
+    A askew = Ar<A>::mul(S, c.inv_h2);
+    A au = Ar<A>::add(askew, Ar<A>::mul(c.adiag, u));
+    return Ar<A>::sub(f, au);
+}
+
+// neighbour sum with out-of-range neighbours reading 0 (cpu-raw.lua:36-39)
+template <int DIM, typename R, typename A>
+__device__ __forceinline__ A stencil_sum(const R *u, int i, int j, int k, int L, size_t idx)
+{
+    const size_t sL = (size_t)L;
+    A xl = i > 0 ? (A)u[idx - 1] : (A)0;
+    A xr = i < L - 1 ? (A)u[idx + 1] : (A)0;
+    A yl = j > 0 ? (A)u[idx - sL] : (A)0;
+    A yr = j < L - 1 ? (A)u[idx + sL] : (A)0;
+    A S = Ar<A>::add(Ar<A>::add(Ar<A>::add(xl, xr), yl), yr);
+    if (DIM == 3) {
+        const size_t sLL = sL * sL;
+        A zl = k > 0 ? (A)u[idx - sLL] : (A)0;
+        A zr = k < L - 1 ? (A)u[idx + sLL] : (A)0;
+        S = Ar<A>::add(Ar<A>::add(S, zl), zr);
+    }
+    return S;
+}
+
+}  // namespace mg

@@ -1,0 +1,231 @@
+--[[
+multigrid-poisson/cuda.lua -- LuaJIT class that puts libmgpoisson.so (B200, sm_100a CUDA)
+behind the solver interface of thenumbernine/lua-multigrid-poisson:
+
+	local cl = require 'multigrid-poisson.cuda'      -- test/test.lua:53
+	local multigrid = cl(size, real, cpuDepth)        -- test/test.lua:54
+	multigrid:run()                                   -- test/test.lua:56
+
+so adding 'cuda' to `cols` in test/test.lua:8-14 is the whole integration. It mirrors
+MultigridCPURaw (cpu-raw.lua:118-258) / MultigridGPU (gpu.lua:18-375): fields size, real,
+smooth, accuracy, debugging; methods init, run, twoGrid, inPlaceIterativeSolver; buffers
+f, psi, psiOld, errorBuf, tmpU, rs[L], Rs[L], vs[L], Vs[L] (device pointers).
+
+NOT EXECUTED in the build environment (no Lua runtime there); the same C ABI is exercised by
+the Python mirror lua-multigrid-poisson_b200/__init__.py. Kept declarative on purpose.
+The ffi.cdef text below is the MGPOISSON_CDEF block of include/mgpoisson.h, verbatim.
+--]]
+local ffi = require 'ffi'
+local class = require 'ext.class'
+local math = require 'ext.math'
+
+ffi.cdef[[
+typedef struct mg_ctx mg_ctx;
+
+/* real_kind: storage type / arithmetic type of every field.
+ *  MG_REAL_F64       double / double   cpu-raw.lua default (cpu-raw.lua:143), gpu.lua with fp64
+ *  MG_REAL_F32       float  / float    gpu.lua on an fp32-only device (gpu.lua:32,39)
+ *  MG_REAL_F32_ACC64 float  / double   cpu-raw.lua with real='float' (LuaJIT evaluates in double)
+ */
+enum { MG_REAL_F64 = 0, MG_REAL_F32 = 1, MG_REAL_F32_ACC64 = 2 };
+
+/* which: the reference's public buffers. `level` is the grid width L of that level
+ * (ignored for the five full-size buffers). */
+enum {
+    MG_BUF_F = 0, MG_BUF_PSI = 1, MG_BUF_PSIOLD = 2, MG_BUF_ERRORBUF = 3, MG_BUF_TMPU = 4,
+    MG_BUF_r = 5, MG_BUF_R = 6, MG_BUF_v = 7, MG_BUF_V = 8
+};
+
+/* mode of mg_vcycle / mg_step / mg_run:
+ *  MG_MODE_FUSED   production path: temporally blocked smoother, residual+restriction and
+ *                  prolongation+add fused into the smoother passes, persistent kernel for
+ *                  the small levels, ping-pong instead of copy-back. rs[L]/vs[L] are never
+ *                  materialised. Per-point arithmetic is identical to MG_MODE_REFSEQ.
+ *  MG_MODE_REFSEQ  one kernel per reference operator in the reference's order, including the
+ *                  tmpU copy-back (cpu-raw.lua:176-237); materialises rs[L], vs[L]; supports
+ *                  the stage trace. This is the `debugging = true` path. */
+enum { MG_MODE_FUSED = 0, MG_MODE_REFSEQ = 1 };
+
+enum {
+    MG_OK = 0, MG_EINVAL = -1, MG_ECUDA = -2, MG_ENOMEM = -3, MG_ESTATE = -4, MG_EUNSUPPORTED = -5
+};
+
+/* ---- lifetime (replaces Class(size, real, cpuDepth): cpu-raw.lua:142-174, gpu.lua:26-245).
+ * Allocates the grid hierarchy in one device arena, zero-fills it once, and runs initCells
+ * (point source, psi = -f). dim = 2 is the reference; dim = 3 is this project's extension.
+ * smooth <= 0 selects the reference default 7 (cpu-raw.lua:123). device < 0 = current device. */
+int mg_create(int dim, int size, int real_kind, int smooth, int device, mg_ctx **out);
+int mg_destroy(mg_ctx *ctx);
+const char *mg_last_error(mg_ctx *ctx);      /* ctx may be NULL: error of a failed mg_create */
+const char *mg_version(void);
+
+/* ---- knobs */
+int mg_set_mode(mg_ctx *ctx, int mode);
+int mg_set_stream(mg_ctx *ctx, void *cuda_stream);   /* borrow a cudaStream_t (NULL = own) */
+/* fused-path tuning: tb = Jacobi sweeps per smoother pass at the tiled levels (1..4),
+ * small_L = largest level width handled by the persistent small-level kernel,
+ * use_graph = replay the V-cycle from a CUDA graph. Negative = keep. */
+int mg_set_tuning(mg_ctx *ctx, int tb, int small_L, int use_graph);
+int mg_get_info(mg_ctx *ctx, int *dim, int *size, int *real_kind, int *smooth, int *nlevels,
+                uint64_t *arena_bytes);
+
+/* ---- data movement (replaces enqueueReadBuffer / enqueueWriteBuffer and `.buffer`) */
+int mg_init_cells(mg_ctx *ctx);                               /* cpu-raw.lua:8-20,173 */
+int mg_zero_corrections(mg_ctx *ctx);                         /* Vs[*] = 0 (cpu.lua:138 variant) */
+int mg_upload(mg_ctx *ctx, int which, int level, const void *host, size_t bytes);
+int mg_download(mg_ctx *ctx, int which, int level, void *host, size_t bytes);
+void *mg_device_ptr(mg_ctx *ctx, int which, int level);       /* NULL if not materialised */
+void *mg_host_alloc(size_t bytes);                            /* pinned host memory for upload/download */
+int mg_host_free(void *p);
+
+/* ---- the hot path */
+int mg_vcycle(mg_ctx *ctx);                                   /* twoGrid(1/size, psi, f, size) */
+int mg_vcycle_async(mg_ctx *ctx);                             /* same, no stream sync on return */
+int mg_synchronize(mg_ctx *ctx);
+int mg_step(mg_ctx *ctx, double *err);                        /* cpu-raw.lua:246-254 */
+int mg_run(mg_ctx *ctx, int max_cycles, double accuracy, double *errs, int *n_done);
+                                                              /* cpu-raw.lua:239-258 */
+/* host-buffer entry point: upload f and psi, one mg_step, download psi. */
+int mg_step_host(mg_ctx *ctx, const void *f_host, void *psi_host, double *err);
+/* true residual RMS ||f - A psi|| / sqrt(N) (not in the reference; SURVEY F6) */
+int mg_residual_norm(mg_ctx *ctx, double *rms);
+
+/* ---- per-operator entry points on device pointers (rows a1-a7 of SURVEY section 8) */
+int mg_twogrid(mg_ctx *ctx, double h, void *u, const void *f, int L);        /* cpu-raw.lua:186 */
+int mg_smooth(mg_ctx *ctx, int L, void *u, const void *f, double h, int n);  /* n x cpu-raw.lua:176 */
+int mg_jacobi(mg_ctx *ctx, int L, void *dest, const void *u, const void *f, double h);
+int mg_residual(mg_ctx *ctx, int L, void *r, const void *f, const void *u, double h);
+int mg_restrict(mg_ctx *ctx, int L2, void *R, const void *r);
+int mg_prolong(mg_ctx *ctx, int L2, void *v, const void *V);
+int mg_add_to(mg_ctx *ctx, size_t n, void *u, const void *v);
+int mg_frob_err(mg_ctx *ctx, double *err);                   /* cpu-raw.lua:249-254 */
+/* fused building blocks of MG_MODE_FUSED, exposed so each can be checked against the
+ * composition of reference operators it replaces:
+ *   mg_smooth_residual_restrict: n sweeps on u, then R = restrict(f - A u)
+ *   mg_prolong_add_smooth:       u += prolong(V), then n sweeps on u                     */
+int mg_smooth_residual_restrict(mg_ctx *ctx, int L, void *u, const void *f, double h, int n,
+                                void *R);
+int mg_prolong_add_smooth(mg_ctx *ctx, int L, void *u, const void *f, double h, int n,
+                          const void *V);
+
+/* ---- stage trace: the reference's `debugging` dumps (cpu-raw.lua:126-140) as records.
+ * Only MG_MODE_REFSEQ records. name is one of 'f','u','r','R','V','v'. */
+int mg_trace_enable(mg_ctx *ctx, int on);
+int mg_trace_clear(mg_ctx *ctx);
+size_t mg_trace_count(mg_ctx *ctx);
+int mg_trace_get(mg_ctx *ctx, size_t i, char *name, int *L, const void **host_data, size_t *bytes);
+
+/* ---- measurement helpers */
+/* run n V-cycles back to back on the handle's stream between two CUDA events */
+int mg_time_vcycles(mg_ctx *ctx, int n, float *ms_total);
+/* kernels launched by this handle since creation (graph replays count their nodes) */
+uint64_t mg_launch_count(mg_ctx *ctx);
+/* one fused V-cycle without the graph, a CUDA-event pair around every launch; fills up to cap
+ * records. kind: 0 smoother pass, 1 residual+restrict, 2 persistent small-level kernel,
+ * 3 prolong+add, 4 copy, 5 smoother pass with fused prolong+add, 6 smoother pass with fused
+ * residual+restrict. L = level width, sweeps = Jacobi sweeps done by that launch. */
+int mg_profile_vcycle(mg_ctx *ctx, int cap, int *kind, int *L, int *sweeps, float *ms, int *n);
+
+/* ---- multi-GPU slabs (one handle per GPU; see INTEGRATION.md). The domain is cut along the
+ * slowest axis into nranks slabs; rank r owns planes [r*size/nranks, (r+1)*size/nranks).
+ * Peers are attached by CUDA IPC handle (other process) or by pointer (same process). */
+int mg_create_slab(int dim, int size, int real_kind, int smooth, int device, int rank, int nranks,
+                   mg_ctx **out);
+int mg_slab_ipc_size(void);
+int mg_slab_export(mg_ctx *ctx, void *ipc_blob, size_t bytes);
+int mg_slab_attach(mg_ctx *ctx, int peer_rank, const void *ipc_blob, size_t bytes);
+int mg_slab_attach_local(mg_ctx *ctx, int peer_rank, mg_ctx *peer);
+]]
+
+local lib = ffi.load(os.getenv'MGPOISSON_LIB' or 'mgpoisson')
+
+local realKinds = {double = lib.MG_REAL_F64, float = lib.MG_REAL_F32, float_acc64 = lib.MG_REAL_F32_ACC64}
+local ctypes = {double = 'double', float = 'float', float_acc64 = 'float'}
+
+local function check(self, rc)
+	if rc ~= 0 then
+		error('libmgpoisson: '..ffi.string(lib.mg_last_error(self and self.handle or nil))..' ('..rc..')')
+	end
+end
+
+local MultigridCUDA = class()
+
+MultigridCUDA.debugging = false		-- cpu-raw.lua:121
+MultigridCUDA.smooth = 7			-- cpu-raw.lua:123
+MultigridCUDA.accuracy = 1e-10		-- cpu-raw.lua:124
+MultigridCUDA.maxiter = 2			-- cpu-raw.lua:245 `for iter=1,2`
+MultigridCUDA.dim = 2				-- 3 = this library's extension
+
+-- level table: self.rs[L] etc. resolve to device pointers on demand (cpu-raw.lua:155-164)
+local function levelTable(self, which)
+	return setmetatable({}, {__index = function(_, L)
+		return lib.mg_device_ptr(self.handle, which, L)
+	end})
+end
+
+function MultigridCUDA:init(size, real, cpuDepth)
+	self.real = real or 'double'		-- cpu-raw.lua:143
+	self.size = size
+	local out = ffi.new'mg_ctx*[1]'
+	check(nil, lib.mg_create(self.dim, size, assert(realKinds[self.real], 'unknown real'), self.smooth, -1, out))
+	self.handle = ffi.gc(out[0], lib.mg_destroy)
+	if cpuDepth then	-- cpu-gpu.lua:11-15: levels L <= 2^cpuDepth go to the small-level executor
+		check(self, lib.mg_set_tuning(self.handle, -1, math.min(bit.lshift(1, cpuDepth), 256, size), -1))
+	end
+	if self.debugging then
+		check(self, lib.mg_set_mode(self.handle, lib.MG_MODE_REFSEQ))
+	end
+	for name,which in pairs{f=lib.MG_BUF_F, psi=lib.MG_BUF_PSI, psiOld=lib.MG_BUF_PSIOLD,
+							errorBuf=lib.MG_BUF_ERRORBUF, tmpU=lib.MG_BUF_TMPU} do
+		self[name] = {buffer = lib.mg_device_ptr(self.handle, which, size)}
+	end
+	self.rs = levelTable(self, lib.MG_BUF_r)
+	self.Rs = levelTable(self, lib.MG_BUF_R)
+	self.vs = levelTable(self, lib.MG_BUF_v)
+	self.Vs = levelTable(self, lib.MG_BUF_V)
+end
+
+-- host <-> device, replacing enqueueReadBuffer/enqueueWriteBuffer (gpu.lua:263-267, cpu-gpu.lua:26-48)
+function MultigridCUDA:getbuffer(which, L)
+	local n = L^self.dim
+	local cpuMem = ffi.new(ctypes[self.real]..'[?]', n)
+	check(self, lib.mg_download(self.handle, which, L, cpuMem, n * ffi.sizeof(ctypes[self.real])))
+	return cpuMem
+end
+function MultigridCUDA:setbuffer(which, L, cpuMem)
+	check(self, lib.mg_upload(self.handle, which, L, cpuMem, L^self.dim * ffi.sizeof(ctypes[self.real])))
+end
+
+function MultigridCUDA:inPlaceIterativeSolver(L, u, f, h)		-- cpu-raw.lua:176-184
+	check(self, lib.mg_smooth(self.handle, L, u, f, h, 1))
+end
+
+function MultigridCUDA:twoGrid(h, u, f, L)						-- cpu-raw.lua:186-237
+	check(self, lib.mg_twogrid(self.handle, h, u, f, L))
+end
+
+function MultigridCUDA:step()									-- cpu.lua:196-206
+	local err = ffi.new'double[1]'
+	check(self, lib.mg_step(self.handle, err))
+	return err[0]
+end
+
+function MultigridCUDA:run()									-- cpu-raw.lua:239-258
+	print('#iter','err')
+	for iter=1,self.maxiter do
+		local err = self:step()
+		print(iter, err)
+		if err < self.accuracy or not math.isfinite(err) then break end
+	end
+end
+
+-- cpu.lua:208-216 API shape (used by test/converge-multigrid-vs-krylov.lua:20-29)
+function MultigridCUDA:solve()
+	for iter=1,(self.maxiter or 1000) do
+		local err = self:step()
+		if self.errorCallback and self.errorCallback(iter, err) then break end
+		if err < (self.epsilon or self.accuracy) or not math.isfinite(err) then break end
+	end
+end
+
+return MultigridCUDA

@@ -1,0 +1,199 @@
+"""-m gpu: the V-cycle (row a8), hierarchy (a9), driver + error metric (a11) through the C ABI
+against the CPU oracle and the committed golden fixtures."""
+import glob
+import io
+import os
+
+import numpy as np
+import pytest
+
+from gpu_util import KINDS, assert_bits_equal, rand_field, to_dev, to_host
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def compare_hierarchy(s, o, orc, what):
+    assert_bits_equal(s.psi.download(), o.psi, f"{what} psi")
+    L = s.size // 2
+    while L >= 1:
+        assert_bits_equal(s.Rs[L].download(), o.buffer(orc.BUF_R, L), f"{what} Rs[{L}]")
+        assert_bits_equal(s.Vs[L].download(), o.buffer(orc.BUF_V, L), f"{what} Vs[{L}]")
+        L //= 2
+
+
+@pytest.mark.parametrize("real", KINDS)
+@pytest.mark.parametrize("dim,size", [(2, 1), (2, 2), (2, 16), (3, 2), (3, 8)])
+def test_refseq_trace_matches_oracle_stage_by_stage(mgp, orc, dim, size, real):
+    """The reference's own cross-variant check (debug dumps f,u,r,R,V,v per level,
+    cpu-raw.lua:126-140,192-235), record by record, two cycles."""
+    s = mgp.MultigridCUDA(size, real, dim=dim, out=False)
+    s.set_debugging(True)
+    o = orc.Oracle(size, real, dim)
+    o.trace_enable()
+    for cyc in range(2):
+        es, eo = s.step(), o.step()
+        assert abs(es - eo) <= 1e-12 * abs(eo) + 1e-300
+    ts, to = s.trace(), o.trace()
+    assert [(n, L) for n, L, _ in ts] == [(n, L) for n, L, _ in to]
+    for i, ((n, L, a), (_, _, b)) in enumerate(zip(ts, to)):
+        assert_bits_equal(a, b, f"trace[{i}] {n} L={L}")
+    for nm in ("tmpU", "errorBuf", "psiOld"):
+        assert_bits_equal(getattr(s, nm).download(), o.buffer(getattr(orc, "BUF_" + nm.upper()), size), nm)
+    L = size
+    while L >= 1:
+        assert_bits_equal(s.rs[L].download(), o.buffer(orc.BUF_r, L), f"rs[{L}]")
+        assert_bits_equal(s.vs[L].download(), o.buffer(orc.BUF_v, L), f"vs[{L}]")
+        L //= 2
+    s.close()
+
+
+@pytest.mark.parametrize("real", KINDS)
+@pytest.mark.parametrize("dim,size", [(2, 64), (2, 512), (3, 32), (3, 128)])
+@pytest.mark.parametrize("mode", ["fused", "refseq"])
+def test_vcycles_match_oracle(mgp, orc, dim, size, real, mode):
+    s = mgp.MultigridCUDA(size, real, dim=dim, out=False)
+    if mode == "refseq":
+        s.set_mode(mgp.MODE_REFSEQ)
+    o = orc.Oracle(size, real, dim, nthreads=8)
+    for cyc in range(3):
+        es, eo = s.step(), o.step()
+        assert abs(es - eo) <= 1e-12 * abs(eo), (cyc, es, eo)
+        compare_hierarchy(s, o, orc, f"cycle {cyc + 1}")
+    assert abs(s.residual_norm() - o.residual_rms()) <= 1e-12 * o.residual_rms()
+    s.close()
+
+
+@pytest.mark.parametrize("dim,size,real", [(2, 256, "double"), (3, 64, "float"), (3, 64, "double")])
+def test_random_rhs_and_guess(mgp, orc, dim, size, real):
+    rng = np.random.default_rng(1234)          # seeded random RHS
+    s = mgp.MultigridCUDA(size, real, dim=dim, out=False)
+    o = orc.Oracle(size, real, dim, nthreads=8)
+    f = rand_field(rng, dim, size, s.dtype) * s.dtype(size * size)
+    psi = rand_field(rng, dim, size, s.dtype)
+    s.f.upload(f); s.psi.upload(psi)
+    o.f[...] = f; o.psi[...] = psi
+    for cyc in range(2):
+        es, eo = s.step(), o.step()
+        assert abs(es - eo) <= 1e-12 * abs(eo)
+    compare_hierarchy(s, o, orc, "random rhs")
+    s.close()
+
+
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "*.npz"))),
+                         ids=lambda p: os.path.basename(p)[:-4])
+def test_cuda_matches_golden_fixtures(mgp, path):
+    g = np.load(path)
+    dim, size, kind, cycles = (int(x) for x in g["meta"])
+    s = mgp.MultigridCUDA(size, kind, dim=dim, out=False)
+    for c in range(cycles):
+        e = s.step()
+        assert abs(e - g["errs"][c]) <= 1e-12 * g["errs"][c]
+        if c == 0:
+            assert_bits_equal(s.psi.download(), g["psi_first"], "psi after cycle 1")
+    assert_bits_equal(s.psi.download(), g["psi_last"], "psi after last cycle")
+    L = size // 2
+    while L >= 1:
+        assert_bits_equal(s.Rs[L].download(), g[f"R{L}"], f"Rs[{L}]")
+        assert_bits_equal(s.Vs[L].download(), g[f"V{L}"], f"Vs[{L}]")
+        L //= 2
+    assert abs(s.residual_norm() - float(g["residual_rms"])) <= 1e-12 * float(g["residual_rms"])
+    s.close()
+
+
+@pytest.mark.parametrize("dim,size", [(2, 256), (3, 64)])
+def test_tuning_knobs_do_not_change_a_single_bit(mgp, dim, size):
+    """temporal-blocking depth, small-level threshold and graph replay are schedule choices;
+    per-point arithmetic is shared (mg_math.cuh), so every setting gives identical fields."""
+    ref = None
+    for tb in (1, 2, 3, 4):
+        for small_L in (1, 4, 16, 64):
+            for graph in (0, 1):
+                if small_L > size or (tb > 1 and graph == 0 and small_L != 16):
+                    continue
+                s = mgp.MultigridCUDA(size, "float", dim=dim, out=False)
+                s.set_tuning(tb=tb, small_L=small_L, use_graph=graph)
+                errs = [s.step() for _ in range(3)]
+                psi = s.psi.download()
+                if ref is None:
+                    ref = (errs, psi)
+                else:
+                    assert errs == ref[0], (tb, small_L, graph)
+                    assert_bits_equal(psi, ref[1], f"tb={tb} small_L={small_L} graph={graph}")
+                s.close()
+
+
+def test_run_contract(mgp, orc):
+    """cpu-raw.lua:239-258: at most 2 cycles, `#iter err` table, stop on err < accuracy."""
+    buf = io.StringIO()
+    s = mgp.MultigridCUDA(64, None, 3, out=buf)          # cl(size, real=nil, cpuDepth) test/test.lua:54
+    assert s.real == "double"
+    errs = s.run()
+    o = orc.Oracle(64, "double", 2)
+    want = o.run()
+    assert len(errs) == 2 and np.allclose(errs, want, rtol=1e-12, atol=0)
+    lines = buf.getvalue().splitlines()
+    assert lines[0] == "#iter\terr" and lines[1].startswith("1\t15402.468010") and len(lines) == 3
+    assert_bits_equal(s.psi.download(), o.psi, "psi after run()")
+    s2 = mgp.MultigridCUDA(64, out=False)
+    assert len(s2.run(max_cycles=5, accuracy=1e3)) == 2   # 800.68 < 1e3 stops it
+    s.close(); s2.close()
+
+
+def test_corrections_persist_between_cycles(mgp, orc):
+    # Vs[L] carries over; zeroing it (cpu.lua:138) gives a different cycle 2
+    a, b = mgp.MultigridCUDA(32, out=False), mgp.MultigridCUDA(32, out=False)
+    a.step(); b.step()
+    b.zero_corrections()
+    a.step(); b.step()
+    assert not np.array_equal(a.psi.download(), b.psi.download())
+    o = orc.Oracle(32)
+    o.step(); o.step()
+    assert_bits_equal(a.psi.download(), o.psi, "persisting V")
+
+
+def test_twogrid_on_a_sub_level_and_user_buffers(mgp, orc):
+    # obj:twoGrid(h, u, f, L) on caller buffers at L < size (what cpu-gpu.lua:35 does)
+    rng = np.random.default_rng(8)
+    s = mgp.MultigridCUDA(128, "double", out=False)
+    o = orc.Oracle(128, "double")
+    for mode in (mgp.MODE_FUSED, mgp.MODE_REFSEQ):
+        s.set_mode(mode)
+        for L in (1, 2, 8, 32):
+            u, f = rand_field(rng, 2, L, np.float64), rand_field(rng, 2, L, np.float64) * L * L
+            du, df = to_dev(u), to_dev(f)
+            s.twoGrid(1.0 / L, du, df, L)
+            uo = u.copy()
+            o.two_grid(1.0 / L, uo, f.copy(), L)
+            assert_bits_equal(to_host(du), uo, f"twoGrid L={L} mode={mode}")
+
+
+def test_host_buffer_entry_point(mgp, orc):
+    s = mgp.MultigridCUDA(64, "float", dim=3, out=False)
+    o = orc.Oracle(64, "float", 3, nthreads=8)
+    f = mgp.PinnedArray((64,) * 3, np.float32)
+    psi = mgp.PinnedArray((64,) * 3, np.float32)
+    f.array[...] = o.f; psi.array[...] = o.psi
+    for _ in range(2):
+        e = s.step_host(f.array, psi.array)
+        eo = o.step()
+        assert abs(e - eo) <= 1e-12 * eo
+        assert_bits_equal(psi.array, o.psi, "psi via host buffers")
+    f.free(); psi.free(); s.close()
+
+
+def test_fp32_arithmetic_within_stated_tolerance_of_cpu_raw_float(mgp, orc):
+    """north_star: fp32 ~1e-5 relative to the initial residual. MG_REAL_F32 (fp32 arithmetic)
+    against cpu-raw.lua's float mode (fp32 storage, double arithmetic)."""
+    for dim, size in ((2, 256), (3, 64)):
+        s = mgp.MultigridCUDA(size, "float", dim=dim, out=False)
+        o = orc.Oracle(size, "float_acc64", dim, nthreads=8)
+        r0 = o.residual_rms()
+        for _ in range(3):
+            es, eo = s.step(), o.step()
+            assert abs(es - eo) <= 1e-5 * eo
+        # residual fields: |r_cuda - r_ref|_rms <= 1e-5 * |r_0|_rms
+        assert abs(s.residual_norm() - o.residual_rms()) <= 1e-5 * r0
+        dpsi = s.psi.download().astype(np.float64) - o.psi
+        assert np.sqrt(np.mean(dpsi**2)) <= 1e-5 * np.sqrt(np.mean(o.psi.astype(np.float64)**2))
+        s.close()
