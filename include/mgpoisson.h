@@ -77,10 +77,14 @@ const char *mg_version(void);
 /* ---- knobs */
 int mg_set_mode(mg_ctx *ctx, int mode);
 int mg_set_stream(mg_ctx *ctx, void *cuda_stream);   /* borrow a cudaStream_t (NULL = own) */
-/* fused-path tuning: tb = Jacobi sweeps per smoother pass at the tiled levels (1..4),
- * small_L = largest level width handled by the persistent small-level kernel,
- * use_graph = replay the V-cycle from a CUDA graph. Negative = keep. */
+/* fused-path tuning: tb = Jacobi sweeps per smoother pass of the streaming (TMA) smoother
+ * (1..4; 0 = untiled one-sweep kernels), small_L = largest level width handled by the
+ * persistent small-level kernel, use_graph = replay the V-cycle from a CUDA graph.
+ * Negative = keep. None of these changes a single bit of any result. */
 int mg_set_tuning(mg_ctx *ctx, int tb, int small_L, int use_graph);
+/* named integer options: "tb", "small_L", "graph", "stream_min_L" (smallest level width
+ * given to the streaming smoother), "tz" (planes per CTA of the streaming smoother; 0 = auto) */
+int mg_set_option(mg_ctx *ctx, const char *name, int value);
 int mg_get_info(mg_ctx *ctx, int *dim, int *size, int *real_kind, int *smooth, int *nlevels,
                 uint64_t *arena_bytes);
 

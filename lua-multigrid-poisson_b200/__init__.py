@@ -88,6 +88,7 @@ def lib():
         "mg_set_mode": (i, [vp, i]),
         "mg_set_stream": (i, [vp, vp]),
         "mg_set_tuning": (i, [vp, i, i, i]),
+        "mg_set_option": (i, [vp, C.c_char_p, i]),
         "mg_get_info": (i, [vp, pi, pi, pi, pi, pi, C.POINTER(u64)]),
         "mg_init_cells": (i, [vp]),
         "mg_zero_corrections": (i, [vp]),
@@ -260,6 +261,9 @@ class MultigridCUDA:
 
     def set_tuning(self, tb=-1, small_L=-1, use_graph=-1):
         self._ck(lib().mg_set_tuning(self._h, tb, small_L, use_graph))
+
+    def set_option(self, name, value):
+        self._ck(lib().mg_set_option(self._h, name.encode(), int(value)))
 
     def info(self):
         v = [C.c_int() for _ in range(5)]

@@ -90,11 +90,26 @@ int mg_set_stream(mg_ctx *ctx, void *cuda_stream)
 int mg_set_tuning(mg_ctx *ctx, int tb, int small_L, int use_graph)
 {
     CTX_OR_FAIL(ctx);
-    if (tb > 4) return ctx->fail(MG_EINVAL, "tb must be 1..4");
+    if (tb > 4) return ctx->fail(MG_EINVAL, "tb must be 0..4");
     if (small_L > (1 << (SMALL_MAX_LEVELS - 1))) return ctx->fail(MG_EINVAL, "small_L too large");
-    if (tb > 0) ctx->tb = tb;
+    if (tb >= 0) ctx->tb = tb;
     if (small_L >= 0) ctx->small_L = small_L;
     if (use_graph >= 0) ctx->use_graph = use_graph;
+    ctx->drop_graph();
+    return MG_OK;
+}
+
+int mg_set_option(mg_ctx *ctx, const char *name, int value)
+{
+    CTX_OR_FAIL(ctx);
+    if (!name) return MG_EINVAL;
+    std::string n(name);
+    if (n == "tb") { if (value < 0 || value > 4) return ctx->fail(MG_EINVAL, "tb must be 0..4"); ctx->tb = value; }
+    else if (n == "small_L") { if (value < 1 || value > (1 << (SMALL_MAX_LEVELS - 1))) return ctx->fail(MG_EINVAL, "bad small_L"); ctx->small_L = value; }
+    else if (n == "graph") ctx->use_graph = value != 0;
+    else if (n == "stream_min_L") ctx->stream_min_L = value < 64 ? 64 : value;
+    else if (n == "tz") ctx->tz_override = value;
+    else return ctx->fail(MG_EINVAL, "mg_set_option: unknown option");
     ctx->drop_graph();
     return MG_OK;
 }

@@ -6,7 +6,9 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <string>
+#include <tuple>
 #include <vector>
 
 #include "../../include/mgpoisson.h"
@@ -14,6 +16,7 @@
 #include "mg_math.cuh"
 #include "mg_ops_ref.cuh"
 #include "mg_small.cuh"
+#include "mg_stream3d.cuh"
 
 namespace mg {
 
@@ -51,6 +54,11 @@ struct mg_ctx {
     int dim = 0, size = 0, real_kind = 0, smooth = 7, device = 0, nlevels = 0, rank = 0, nranks = 1;
     size_t elem = 0, N = 0;
     int mode = MG_MODE_FUSED, tb = 1, small_L = 0, use_graph = 1;
+    int stream_min_L = 128;  // smallest level width handled by the streaming (TMA) smoother
+    int tz_override = 0;     // planes per CTA of the streaming smoother (0 = cost model)
+    // TMA descriptors of the source fields, keyed by (pointer, level width, box x, box y)
+    std::map<std::tuple<const void *, int, int, int>, CUtensorMap> tmaps;
+    int tensor_map(const void *base, int L, int box_x, int box_y, const CUtensorMap **out);
 
     // ---- grid-hierarchy arena (K-f): one allocation, zero-filled once (cpu-raw.lua:159-171)
     void *arena = nullptr;
@@ -281,10 +289,80 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
     // ------------------------------------------------------------ fused passes
     // n sweeps starting from `cur` (ping-pong with `oth`), the first optionally reading
     // cur + prolong(Vp), followed optionally by Rout = restrict(f - A cur).
+    // ---- streaming (TMA, temporally blocked) smoother passes, 3-D only
+    template <int S, bool PRO, bool RES>
+    int launch_stream3d(mg_ctx *c, int L, R *dst, const R *src, const R *f, const R *Vp, R *Rout, const Coef<A> &cf)
+    {
+        constexpr int TX = 64, TY = 32;
+        typedef Stream3DCfg<R, S, RES, TX, TY> C;
+        const CUtensorMap *map = nullptr;
+        int rc = c->tensor_map(src, L, C::WX, C::WY, &map);
+        if (rc) return rc;
+        auto kern = k_stream3d<R, A, S, PRO, RES, TX, TY>;
+        MG_CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+        // planes per CTA: minimise waves x steps-per-CTA on 148 SMs (one CTA per SM)
+        int TZ = c->tz_override;
+        if (TZ <= 0) {
+            const long tiles = (long)((L + TX - 1) / TX) * ((L + TY - 1) / TY);
+            long best = -1;
+            for (int cand = L; cand >= 8; cand >>= 1) {
+                long ncta = tiles * (L / cand);
+                long cost = ((ncta + 147) / 148) * (cand + 3 * C::H);
+                if (best < 0 || cost < best) { best = cost; TZ = cand; }
+            }
+        }
+        if (TZ > L) TZ = L;
+        TZ &= ~1;
+        dim3 grid((L + TX - 1) / TX, (L + TY - 1) / TY, (L + TZ - 1) / TZ);
+        Stream3DArgs<R> a{dst, f, Vp, Rout, L, TZ};
+        c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : (RES ? MG_K_SWEEP_RESTRICT : MG_K_SWEEP), L, S);
+        kern<<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(*map, a, cf);
+        c->prof_end();
+        MG_LAUNCH_CHECK(c);
+        return MG_OK;
+    }
+    int stream3d_pass(mg_ctx *c, int L, int S, bool pro, bool res, R *dst, const R *src, const R *f,
+                      const R *Vp, R *Rout, const Coef<A> &cf)
+    {
+#define MG_S3D(S_, P_, R_) return launch_stream3d<S_, P_, R_>(c, L, dst, src, f, Vp, Rout, cf)
+        if (!pro && !res) {
+            switch (S) { case 1: MG_S3D(1, false, false); case 2: MG_S3D(2, false, false);
+                         case 3: MG_S3D(3, false, false); case 4: MG_S3D(4, false, false); }
+        } else if (pro && !res) {
+            switch (S) { case 1: MG_S3D(1, true, false); case 2: MG_S3D(2, true, false);
+                         case 3: MG_S3D(3, true, false); case 4: MG_S3D(4, true, false); }
+        } else if (!pro && res) {
+            switch (S) { case 1: MG_S3D(1, false, true); case 2: MG_S3D(2, false, true);
+                         case 3: MG_S3D(3, false, true); }
+        }
+#undef MG_S3D
+        return c->fail(MG_EINVAL, "stream3d_pass: unsupported combination");
+    }
+    int sweeps_stream3d(mg_ctx *c, int L, R *&cur, R *&oth, const R *f, const Coef<A> &cf, int n,
+                        const R *Vp, R *Rout)
+    {
+        const int tb = c->tb;
+        int plan[64], np = 0, rem = n, last = 0;
+        if (Rout) { last = n < 3 ? n : 3; if (last > tb) last = tb; rem = n - last; }
+        if (rem > 0) {
+            int k = (rem + tb - 1) / tb, base = rem / k, extra = rem % k;
+            for (int i = 0; i < k; ++i) plan[np++] = base + (i < extra ? 1 : 0);
+        }
+        if (Rout) plan[np++] = last;
+        for (int i = 0; i < np; ++i) {
+            int rc = stream3d_pass(c, L, plan[i], i == 0 && Vp, i == np - 1 && Rout, oth, cur, f, Vp, Rout, cf);
+            if (rc) return rc;
+            R *t = cur; cur = oth; oth = t;
+        }
+        return MG_OK;
+    }
+
     int sweeps(mg_ctx *c, int lv, R *&cur, R *&oth, const R *f, double h, int n, const R *Vp, R *Rout)
     {
         const int L = 1 << lv;
         const Coef<A> cf = make_coef<A>(DIM, h);
+        if (DIM == 3 && c->tb >= 1 && L >= c->stream_min_L && n >= 1 && !(Vp && Rout && n <= c->tb))
+            return sweeps_stream3d(c, L, cur, oth, f, cf, n, Vp, Rout);
         dim3 b = block_for(L), g = grid_for(DIM, L, b);
         for (int s = 0; s < n; ++s) {
             c->prof_begin(s == 0 && Vp ? MG_K_SWEEP_PROLONG : MG_K_SWEEP, L, 1);
@@ -569,6 +647,43 @@ inline void *mg_ctx::buffer(int which, int level, size_t *cap)
     case MG_BUF_V: return V[lv];
     }
     return nullptr;
+}
+
+// TMA descriptor of a dense L^3 field with a (box_x, box_y, 1) box; out-of-bounds elements are
+// zero-filled, which is the reference's Dirichlet rule (cpu-raw.lua:36-39).
+inline int mg_ctx::tensor_map(const void *base, int L, int box_x, int box_y, const CUtensorMap **out)
+{
+    auto key = std::make_tuple(base, L, box_x, box_y);
+    auto it = tmaps.find(key);
+    if (it != tmaps.end()) { *out = &it->second; return MG_OK; }
+    typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                 const cuuint64_t *, const cuuint32_t *, const cuuint32_t *,
+                                 CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                 CUtensorMapFloatOOBfill);
+    static EncodeFn encode = nullptr;
+    if (!encode) {
+        void *fn = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        MG_CK(this, cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &q));
+        if (!fn || q != cudaDriverEntryPointSuccess) return fail(MG_ECUDA, "cuTensorMapEncodeTiled not available");
+        encode = (EncodeFn)fn;
+    }
+    CUtensorMap m;
+    cuuint64_t gdim[3] = {(cuuint64_t)L, (cuuint64_t)L, (cuuint64_t)L};
+    cuuint64_t gstr[2] = {(cuuint64_t)L * elem, (cuuint64_t)L * L * elem};
+    cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1};
+    cuuint32_t est[3] = {1, 1, 1};
+    CUresult r = encode(&m, elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
+                        const_cast<void *>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);
+        return MG_ECUDA;
+    }
+    auto ins = tmaps.emplace(key, m);
+    *out = &ins.first->second;
+    return MG_OK;
 }
 
 inline void mg_ctx::drop_graph()

@@ -1,0 +1,352 @@
+// mg_stream3d.cuh -- (K-a/K-b/K-c) temporally blocked 3-D Jacobi smoother for sm_100a.
+//
+// One launch performs S Jacobi sweeps (cpu-raw.lua:34-44 semantics, 3-D rules of SURVEY 8(a'))
+// on a level, optionally
+//   PRO: starting from  src + prolong(V)  (expandResidual + addTo, cpu-raw.lua:65-73,83-85)
+//   RES: followed by    Rout = restrict(f - A u)  (calcResidual + reduceResidual, :46-63)
+// reading src once and writing dst once: HBM traffic per launch ~ 3 words/point instead of
+// 3*S (+6 for the transfer operators).
+//
+// Structure ("3.5-D blocking"): a CTA owns an in-plane tile TX x TY plus halo and streams
+// along z. Plane a_t of the source arrives in shared memory by TMA (cp.async.bulk.tensor,
+// mbarrier-signalled, NSLOT-deep ring); TMA's out-of-bounds ZERO FILL is the reference's
+// Dirichlet rule "a neighbour outside the grid reads 0" (cpu-raw.lua:36-39), so domain edges
+// need no branches on load. The S sweeps (+1 residual stage) form a software pipeline of
+// NST stages; at step t stage s consumes plane a_t - 2(s-1) of stage s-1's output from
+// shared memory and emits its own plane one below it. A thread owns VX x 2 columns for the
+// whole launch and keeps, per stage, two registers per column:
+//   prev = centre value of the previous plane            (the z-1 neighbour)
+//   acc  = ((xl+xr)+yl)+yr + zl of the pending plane      (waiting for its z+1 neighbour)
+// so each plane of each stage is read from shared memory exactly once (4 x LDS.128 +
+// 4 x LDS.32 per 8 points) and ONE __syncthreads() per step serves all stages.
+// The summation order ((((xl+xr)+yl)+yr)+zl)+zr is preserved, so results are bit-identical
+// to the one-sweep-per-launch kernels (all arithmetic from mg_math.cuh).
+//
+// Cells outside the grid must stay exactly 0 at every stage: in-plane via a per-thread
+// bit mask, whole planes via a CTA-uniform test. Values near the tile edge that lack a
+// neighbour are garbage by construction and never reach the H-deep interior (H = NST).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "mg_math.cuh"
+
+namespace mg {
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra DONE_%=;\n"
+        "bra WAIT_%=;\n"
+        "DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// orders this CTA's earlier generic-proxy accesses to shared memory (made visible to the
+// calling thread by a preceding barrier) before later async-proxy (TMA) accesses
+__device__ __forceinline__ void fence_proxy_async_smem()
+{
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int x, int y, int z,
+                                            uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(smem_dst)),
+        "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// ------------------------------------------------------------------ vector access
+template <typename R> struct Vec;
+template <> struct Vec<float> {
+    static constexpr int N = 4;
+    typedef float4 T;
+    static __device__ __forceinline__ void unpack(const T &v, float *o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
+    static __device__ __forceinline__ T pack(const float *o) { return make_float4(o[0], o[1], o[2], o[3]); }
+    static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+};
+template <> struct Vec<double> {
+    static constexpr int N = 2;
+    typedef double2 T;
+    static __device__ __forceinline__ void unpack(const T &v, double *o) { o[0] = v.x; o[1] = v.y; }
+    static __device__ __forceinline__ T pack(const double *o) { return make_double2(o[0], o[1]); }
+    static __device__ __forceinline__ T zero() { return make_double2(0., 0.); }
+};
+
+template <typename R, int S, bool RES, int TX, int TY> struct Stream3DCfg {
+    static constexpr int VX = Vec<R>::N;
+    static constexpr int NST = S + (RES ? 1 : 0);
+    static constexpr int H = NST;
+    static constexpr int HX = (H + VX - 1) / VX * VX;
+    static constexpr int HY = RES ? (H + 1) / 2 * 2 : H;
+    static constexpr int WX = TX + 2 * HX, WY = TY + 2 * HY;
+    static constexpr int UX = WX / VX, UY = WY / 2;
+    static constexpr int NT = UX * UY;
+    static constexpr int NTHREADS = (NT + 31) / 32 * 32;
+    static constexpr int PLANE = WX * WY;
+    static constexpr int PLANE_BYTES = PLANE * (int)sizeof(R);
+    static constexpr int SLOT_BYTES = (PLANE_BYTES + 127) / 128 * 128;
+    static constexpr int NSLOT = 4;
+    static constexpr int NRING = NST - 1;  // intermediate stage outputs, double buffered
+    static constexpr int SMEM_BYTES = NSLOT * SLOT_BYTES + NRING * 2 * SLOT_BYTES + NSLOT * 8 + 128;
+    static_assert(TX % VX == 0 && TY % 2 == 0 && WY % 2 == 0, "tile shape");
+    static_assert(NTHREADS <= 1024, "too many threads");
+};
+
+template <typename R> struct Stream3DArgs {
+    R *dst;           // u after S sweeps
+    const R *f;       // right-hand side of this level
+    const R *Vp;      // PRO: coarse correction Vs[L/2]
+    R *Rout;          // RES: Rs[L/2]
+    int L;            // level width
+    int TZ;           // planes per CTA (even)
+};
+
+template <typename R, typename A, int S, bool PRO, bool RES, int TX, int TY>
+__global__ void __launch_bounds__((Stream3DCfg<R, S, RES, TX, TY>::NTHREADS), 1)
+k_stream3d(const __grid_constant__ CUtensorMap src_map, Stream3DArgs<R> a, Coef<A> cf)
+{
+    typedef Stream3DCfg<R, S, RES, TX, TY> C;
+    typedef typename Vec<R>::T VT;
+    constexpr int VX = C::VX, NST = C::NST, H = C::H, NP = 2 * VX;
+
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    // layout: [NSLOT input slots][NRING*2 stage slots][NSLOT mbarriers]
+    unsigned char *sbase = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
+    auto in_slot = [&](int k) -> R * { return (R *)(sbase + (size_t)k * C::SLOT_BYTES); };
+    auto ring_slot = [&](int s, int par) -> R * {
+        return (R *)(sbase + (size_t)(C::NSLOT + 2 * s + par) * C::SLOT_BYTES);
+    };
+    uint64_t *mbar = (uint64_t *)(sbase + (size_t)(C::NSLOT + 2 * C::NRING) * C::SLOT_BYTES);
+
+    const int tid = threadIdx.x;
+    const bool worker = tid < C::NT;
+    const int ux = worker ? tid % C::UX : 0, uy = worker ? tid / C::UX : 0;
+    const int L = a.L;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = blockIdx.z * a.TZ;
+    const int z1 = min(z0 + a.TZ, L);
+    const int TZ = z1 - z0;
+    const int zb = z0 - H;          // plane index of input step 0
+    const int nin = TZ + 2 * H;     // input planes
+    const int T = TZ + 3 * H - 1;   // steps
+
+    // ---- per-thread geometry (constant over the launch)
+    const int gx0 = x0 - C::HX + VX * ux;          // global x of the first owned point
+    const int gy0 = y0 - C::HY + 2 * uy;           // global y of the first owned row
+    const int off0 = (2 * uy) * C::WX + VX * ux;   // smem offset of row 0 of the unit
+    const int off1 = off0 + C::WX;
+    const int offU = uy == 0 ? off0 : off0 - C::WX;               // row above (clamped: garbage zone)
+    const int offD = uy == C::UY - 1 ? off1 : off1 + C::WX;       // row below
+    const int dl = ux == 0 ? 0 : -1;                               // left neighbour of the first point
+    const int dr = ux == C::UX - 1 ? VX - 1 : VX;                  // right neighbour of the last point
+    const bool xin = gx0 >= 0 && gx0 < L;                          // L % VX == 0: whole group in or out
+    const bool yin0 = gy0 >= 0 && gy0 < L, yin1 = gy0 + 1 >= 0 && gy0 + 1 < L;
+    const bool in0 = worker && xin && yin0, in1 = worker && xin && yin1;
+    // interior of the output tile (what this CTA is responsible for writing)
+    const bool xint = ux >= C::HX / VX && ux < (C::HX + TX) / VX;
+    const bool st0 = in0 && xint && (2 * uy >= C::HY) && (2 * uy < C::HY + TY);
+    const bool st1 = in1 && xint && (2 * uy + 1 >= C::HY) && (2 * uy + 1 < C::HY + TY);
+    const size_t sL = (size_t)L, sLL = sL * sL;
+    const size_t g0 = (size_t)gx0 + sL * (size_t)gy0;              // only used when in-domain
+
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < C::NSLOT; ++k) mbar_init(&mbar[k], 1);
+        mbar_fence_init();
+    }
+    __syncthreads();
+    if (tid == 0) {
+#pragma unroll
+        for (int k = 0; k < C::NSLOT - 1; ++k)
+            if (k < nin) {
+                mbar_expect_tx(&mbar[k], C::PLANE_BYTES);
+                tma_load_3d(in_slot(k), &src_map, x0 - C::HX, y0 - C::HY, zb + k, &mbar[k]);
+            }
+    }
+
+    // PRO: add prolong(V) to the own points of an arrived input slot, in place
+    auto fixup = [&](int t) {
+        if (!PRO || !worker) return;
+        const int p = zb + t;
+        if (p < 0 || p >= L) return;                               // plane outside the grid stays 0
+        R *sl = in_slot(t % C::NSLOT);
+        const int L2 = L >> 1;
+        const size_t cbase = (size_t)(gx0 >> 1) + (size_t)L2 * ((size_t)(gy0 >> 1) + (size_t)L2 * (p >> 1));
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const bool in = r == 0 ? in0 : in1;
+            if (!in) continue;
+            // rows gy0 and gy0+1 share a coarse row only if gy0 is even
+            const size_t crow = (size_t)(gx0 >> 1) + (size_t)L2 * ((size_t)((gy0 + r) >> 1) + (size_t)L2 * (p >> 1));
+            (void)cbase;
+            R u[VX];
+            Vec<R>::unpack(*(const VT *)(sl + (r == 0 ? off0 : off1)), u);
+#pragma unroll
+            for (int i = 0; i < VX; ++i) {
+                R vv = a.Vp[crow + (i >> 1)];
+                u[i] = (R)Ar<A>::add((A)u[i], (A)vv);
+            }
+            *(VT *)(sl + (r == 0 ? off0 : off1)) = Vec<R>::pack(u);
+        }
+    };
+
+    A acc[NST][NP], prev[NST][NP];
+#pragma unroll
+    for (int s = 0; s < NST; ++s)
+#pragma unroll
+        for (int i = 0; i < NP; ++i) { acc[s][i] = (A)0; prev[s][i] = (A)0; }
+    A rpart[VX];  // RES: restriction partial sums of the even plane (VX/2 coarse cells x ... kept per pair)
+#pragma unroll
+    for (int i = 0; i < VX; ++i) rpart[i] = (A)0;
+
+    if (PRO) {
+        mbar_wait(&mbar[0], 0);
+        fixup(0);
+        __syncthreads();
+    }
+
+    for (int t = 0; t < T; ++t) {
+        // (1) refill the slot consumed at step t-1 (all threads passed the barrier ending it)
+        if (tid == 0) {
+            const int k = t + C::NSLOT - 1;
+            if (k < nin) {
+                fence_proxy_async_smem();
+                mbar_expect_tx(&mbar[k % C::NSLOT], C::PLANE_BYTES);
+                tma_load_3d(in_slot(k % C::NSLOT), &src_map, x0 - C::HX, y0 - C::HY, zb + k, &mbar[k % C::NSLOT]);
+            }
+        }
+        // (2) input plane of this step (PRO: it was awaited and fixed up during step t-1)
+        if (!PRO) {
+            if (t < nin) mbar_wait(&mbar[t % C::NSLOT], (uint32_t)((t / C::NSLOT) & 1));
+        }
+
+        // (3) the pipeline stages; stage s = sidx+1
+#pragma unroll
+        for (int sidx = 0; sidx < NST; ++sidx) {
+            const int s = sidx + 1;
+            const bool active = (t >= 3 * sidx) && (t <= nin + s - 2);
+            if (!active || !worker) continue;
+            const bool emit = t >= 3 * s - 1;
+            const int p = zb + t - 2 * sidx - 1;                   // plane emitted (q - 1)
+            const R *in = sidx == 0 ? in_slot(t % C::NSLOT) : ring_slot(sidx - 1, (t - 1) & 1);
+            const bool is_res = RES && s == NST;
+            const bool last_jacobi = s == S;
+
+            // f for the emitted plane (issued early; consumed after the shared-memory work)
+            R fv[NP];
+            const bool pin = p >= 0 && p < L;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) fv[i] = (R)0;
+            if (emit && pin) {
+                if (in0) Vec<R>::unpack(*(const VT *)(a.f + g0 + sLL * (size_t)p), fv);
+                if (in1) Vec<R>::unpack(*(const VT *)(a.f + g0 + sL + sLL * (size_t)p), fv + VX);
+            }
+
+            R c0[VX], c1[VX], up[VX], dn[VX];
+            Vec<R>::unpack(*(const VT *)(in + off0), c0);
+            Vec<R>::unpack(*(const VT *)(in + off1), c1);
+            Vec<R>::unpack(*(const VT *)(in + offU), up);
+            Vec<R>::unpack(*(const VT *)(in + offD), dn);
+            const R l0 = in[off0 + dl], l1 = in[off1 + dl], r0 = in[off0 + dr], r1 = in[off1 + dr];
+
+            R outv[NP];
+#pragma unroll
+            for (int i = 0; i < VX; ++i) {
+                // row 0 of the unit
+                {
+                    const A xl = (A)(i == 0 ? l0 : c0[i - 1]), xr = (A)(i == VX - 1 ? r0 : c0[i + 1]);
+                    const A yl = (A)up[i], yr = (A)c1[i], c = (A)c0[i];
+                    const A part = Ar<A>::add(Ar<A>::add(Ar<A>::add(xl, xr), yl), yr);
+                    const A tot = Ar<A>::add(acc[sidx][i], c);                 // pending plane gets its z+1
+                    const A f_ = (A)fv[i];
+                    A o = is_res ? residual_point<A>(tot, f_, prev[sidx][i], cf) : jacobi_point<3, A>(tot, f_, cf);
+                    outv[i] = (in0 && pin) ? (R)o : (R)0;
+                    acc[sidx][i] = Ar<A>::add(part, prev[sidx][i]);           // this plane gets its z-1
+                    prev[sidx][i] = c;
+                }
+                // row 1 of the unit
+                {
+                    const int j = VX + i;
+                    const A xl = (A)(i == 0 ? l1 : c1[i - 1]), xr = (A)(i == VX - 1 ? r1 : c1[i + 1]);
+                    const A yl = (A)c0[i], yr = (A)dn[i], c = (A)c1[i];
+                    const A part = Ar<A>::add(Ar<A>::add(Ar<A>::add(xl, xr), yl), yr);
+                    const A tot = Ar<A>::add(acc[sidx][j], c);
+                    const A f_ = (A)fv[j];
+                    A o = is_res ? residual_point<A>(tot, f_, prev[sidx][j], cf) : jacobi_point<3, A>(tot, f_, cf);
+                    outv[j] = (in1 && pin) ? (R)o : (R)0;
+                    acc[sidx][j] = Ar<A>::add(part, prev[sidx][j]);
+                    prev[sidx][j] = c;
+                }
+            }
+            if (!emit) continue;
+
+            if (!is_res) {
+                if (s < NST) {  // feed the next stage
+                    R *out = ring_slot(sidx, t & 1);
+                    *(VT *)(out + off0) = Vec<R>::pack(outv);
+                    *(VT *)(out + off1) = Vec<R>::pack(outv + VX);
+                }
+                if (last_jacobi && p >= z0 && p < z1) {
+                    if (st0) *(VT *)(a.dst + g0 + sLL * (size_t)p) = Vec<R>::pack(outv);
+                    if (st1) *(VT *)(a.dst + g0 + sL + sLL * (size_t)p) = Vec<R>::pack(outv + VX);
+                }
+            } else if (p >= z0 && p < z1 && st0 && st1) {
+                // restriction: children in the order i fastest, then j, then k (SURVEY 8(a'))
+                const int L2 = L >> 1;
+                if ((p & 1) == 0) {
+#pragma unroll
+                    for (int cidx = 0; cidx < VX / 2; ++cidx) {
+                        A sacc = Ar<A>::add((A)outv[2 * cidx], (A)outv[2 * cidx + 1]);
+                        sacc = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx]);
+                        rpart[cidx] = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx + 1]);
+                    }
+                } else {
+                    const size_t cb = (size_t)(gx0 >> 1) + (size_t)L2 * ((size_t)(gy0 >> 1) + (size_t)L2 * (p >> 1));
+#pragma unroll
+                    for (int cidx = 0; cidx < VX / 2; ++cidx) {
+                        A sacc = Ar<A>::add(rpart[cidx], (A)outv[2 * cidx]);
+                        sacc = Ar<A>::add(sacc, (A)outv[2 * cidx + 1]);
+                        sacc = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx]);
+                        sacc = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx + 1]);
+                        a.Rout[cb + cidx] = (R)Ar<A>::mul((A).125, sacc);
+                    }
+                }
+            }
+        }
+
+        // (PRO) prepare next step's input plane in place
+        if (PRO && t + 1 < nin) {
+            mbar_wait(&mbar[(t + 1) % C::NSLOT], (uint32_t)(((t + 1) / C::NSLOT) & 1));
+            fixup(t + 1);
+        }
+        __syncthreads();
+    }
+}
+
+}  // namespace mg

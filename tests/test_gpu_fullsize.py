@@ -4,7 +4,7 @@ properties: exact power-of-two scaling (KA4), fused == reference sequence bit-fo
 import numpy as np
 import pytest
 
-from gpu_util import assert_bits_equal
+from gpu_util import err_rtol, assert_bits_equal
 
 pytestmark = pytest.mark.gpu
 
@@ -13,7 +13,7 @@ def test_c3_3d_512_fp32_one_cycle_vs_oracle(mgp, orc):
     s = mgp.MultigridCUDA(512, "float", dim=3, out=False)
     o = orc.Oracle(512, "float", 3, nthreads=orc.lib().orc_max_threads())
     es, eo = s.step(), o.step()
-    assert abs(es - eo) <= 1e-12 * eo
+    assert abs(es - eo) <= err_rtol(s.size ** s.dim) * eo
     assert_bits_equal(s.psi.download(), o.psi, "512^3 psi after 1 cycle")
     assert_bits_equal(s.Rs[256].download(), o.buffer(orc.BUF_R, 256), "Rs[256]")
     assert_bits_equal(s.Vs[256].download(), o.buffer(orc.BUF_V, 256), "Vs[256]")
@@ -25,7 +25,7 @@ def test_c2_2d_4096_fp32_two_cycles_vs_oracle(mgp, orc):
     o = orc.Oracle(4096, "float", 2, nthreads=orc.lib().orc_max_threads())
     for _ in range(2):
         es, eo = s.step(), o.step()
-        assert abs(es - eo) <= 1e-12 * eo
+        assert abs(es - eo) <= err_rtol(s.size ** s.dim) * eo
     assert_bits_equal(s.psi.download(), o.psi, "4096^2 psi after 2 cycles")
     s.close()
 
@@ -35,7 +35,7 @@ def test_c5_2d_2048_fp64_two_cycles_vs_oracle(mgp, orc):
     o = orc.Oracle(2048, "double", 2, nthreads=orc.lib().orc_max_threads())
     for _ in range(2):
         es, eo = s.step(), o.step()
-        assert abs(es - eo) <= 1e-12 * eo
+        assert abs(es - eo) <= err_rtol(s.size ** s.dim) * eo
     assert_bits_equal(s.psi.download(), o.psi, "2048^2 psi after 2 cycles")
     s.close()
 

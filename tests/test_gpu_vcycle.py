@@ -7,7 +7,7 @@ import os
 import numpy as np
 import pytest
 
-from gpu_util import KINDS, assert_bits_equal, rand_field, to_dev, to_host
+from gpu_util import err_rtol, KINDS, assert_bits_equal, rand_field, to_dev, to_host
 
 pytestmark = pytest.mark.gpu
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -33,7 +33,7 @@ def test_refseq_trace_matches_oracle_stage_by_stage(mgp, orc, dim, size, real):
     o.trace_enable()
     for cyc in range(2):
         es, eo = s.step(), o.step()
-        assert abs(es - eo) <= 1e-12 * abs(eo) + 1e-300
+        assert abs(es - eo) <= err_rtol(size ** dim) * abs(eo) + 1e-300
     ts, to = s.trace(), o.trace()
     assert [(n, L) for n, L, _ in ts] == [(n, L) for n, L, _ in to]
     for i, ((n, L, a), (_, _, b)) in enumerate(zip(ts, to)):
@@ -58,9 +58,9 @@ def test_vcycles_match_oracle(mgp, orc, dim, size, real, mode):
     o = orc.Oracle(size, real, dim, nthreads=8)
     for cyc in range(3):
         es, eo = s.step(), o.step()
-        assert abs(es - eo) <= 1e-12 * abs(eo), (cyc, es, eo)
+        assert abs(es - eo) <= err_rtol(size ** dim) * abs(eo), (cyc, es, eo)
         compare_hierarchy(s, o, orc, f"cycle {cyc + 1}")
-    assert abs(s.residual_norm() - o.residual_rms()) <= 1e-12 * o.residual_rms()
+    assert abs(s.residual_norm() - o.residual_rms()) <= err_rtol(size ** dim) * o.residual_rms()
     s.close()
 
 
@@ -75,7 +75,7 @@ def test_random_rhs_and_guess(mgp, orc, dim, size, real):
     o.f[...] = f; o.psi[...] = psi
     for cyc in range(2):
         es, eo = s.step(), o.step()
-        assert abs(es - eo) <= 1e-12 * abs(eo)
+        assert abs(es - eo) <= err_rtol(size ** dim) * abs(eo)
     compare_hierarchy(s, o, orc, "random rhs")
     s.close()
 
@@ -101,18 +101,19 @@ def test_cuda_matches_golden_fixtures(mgp, path):
     s.close()
 
 
-@pytest.mark.parametrize("dim,size", [(2, 256), (3, 64)])
+@pytest.mark.parametrize("dim,size", [(2, 256), (3, 128)])
 def test_tuning_knobs_do_not_change_a_single_bit(mgp, dim, size):
     """temporal-blocking depth, small-level threshold and graph replay are schedule choices;
     per-point arithmetic is shared (mg_math.cuh), so every setting gives identical fields."""
     ref = None
-    for tb in (1, 2, 3, 4):
-        for small_L in (1, 4, 16, 64):
+    for tb in (0, 1, 2, 3, 4):
+        for small_L in (1, 4, 16, 32):
             for graph in (0, 1):
                 if small_L > size or (tb > 1 and graph == 0 and small_L != 16):
                     continue
                 s = mgp.MultigridCUDA(size, "float", dim=dim, out=False)
                 s.set_tuning(tb=tb, small_L=small_L, use_graph=graph)
+                s.set_option("stream_min_L", 64)
                 errs = [s.step() for _ in range(3)]
                 psi = s.psi.download()
                 if ref is None:
@@ -177,7 +178,7 @@ def test_host_buffer_entry_point(mgp, orc):
     for _ in range(2):
         e = s.step_host(f.array, psi.array)
         eo = o.step()
-        assert abs(e - eo) <= 1e-12 * eo
+        assert abs(e - eo) <= err_rtol(64 ** 3) * eo
         assert_bits_equal(psi.array, o.psi, "psi via host buffers")
     f.free(); psi.free(); s.close()
 
