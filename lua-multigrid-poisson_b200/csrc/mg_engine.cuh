@@ -17,6 +17,7 @@
 #include "mg_ops_ref.cuh"
 #include "mg_small.cuh"
 #include "mg_stream3d.cuh"
+#include "mg_warp2d.cuh"
 
 namespace mg {
 
@@ -54,6 +55,9 @@ struct mg_ctx {
     int dim = 0, size = 0, real_kind = 0, smooth = 7, device = 0, nlevels = 0, rank = 0, nranks = 1;
     size_t elem = 0, N = 0;
     int mode = MG_MODE_FUSED, tb = 1, small_L = 0, use_graph = 1;
+    int tb2 = 7;             // 2-D: sweeps per pass of the warp-streaming smoother (0 = untiled)
+    int warp2d_min_L = 128;  // 2-D: smallest level width handled by the warp-streaming smoother
+    int ty_override = 0;     // 2-D: rows per warp work item (0 = cost model)
     int stream_min_L = 128;  // smallest level width handled by the streaming (TMA) smoother
     int tz_override = 0;     // planes per CTA of the streaming smoother (0 = cost model)
     // TMA descriptors of the source fields, keyed by (pointer, level width, box x, box y)
@@ -357,12 +361,68 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         return MG_OK;
     }
 
+    // ---- 2-D warp-streaming smoother passes
+    template <int S, bool PRO, bool RES>
+    int launch_warp2d(mg_ctx *c, int L, R *dst, const R *src, const R *f, const R *Vp, R *Rout, const Coef<A> &cf)
+    {
+        typedef Warp2DCfg<S, RES> C;
+        const int nstrips = (L + C::TXU - 1) / C::TXU;
+        int TY = c->ty_override;
+        if (TY <= 0) {  // rows per work item: waves of 148 SMs x 16 resident warps, times rows streamed
+            long best = -1;
+            for (int cand = L; cand >= 16; cand >>= 1) {
+                long items = (long)nstrips * ((L + cand - 1) / cand);
+                long cost = ((items + 148 * 16 - 1) / (148 * 16)) * (cand + 2 * C::H);
+                if (best < 0 || cost < best) { best = cost; TY = cand; }
+            }
+        }
+        if (TY > L) TY = L;
+        TY &= ~1;
+        const int nitems = nstrips * ((L + TY - 1) / TY);
+        c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : (RES ? MG_K_SWEEP_RESTRICT : MG_K_SWEEP), L, S);
+        k_warp2d<R, A, S, PRO, RES><<<(nitems + 3) / 4, 128, 0, c->stream>>>(dst, src, f, Vp, Rout, L, TY, nstrips, nitems, cf);
+        c->prof_end();
+        MG_LAUNCH_CHECK(c);
+        return MG_OK;
+    }
+    int warp2d_pass(mg_ctx *c, int L, int S, bool pro, bool res, R *dst, const R *src, const R *f,
+                    const R *Vp, R *Rout, const Coef<A> &cf)
+    {
+#define MG_W2D(S_) \
+    case S_: \
+        if (pro) return launch_warp2d<S_, true, false>(c, L, dst, src, f, Vp, Rout, cf); \
+        if (res) return launch_warp2d<S_, false, true>(c, L, dst, src, f, Vp, Rout, cf); \
+        return launch_warp2d<S_, false, false>(c, L, dst, src, f, Vp, Rout, cf);
+        switch (S) { MG_W2D(1) MG_W2D(2) MG_W2D(3) MG_W2D(4) MG_W2D(5) MG_W2D(6) MG_W2D(7) }
+#undef MG_W2D
+        return c->fail(MG_EINVAL, "warp2d_pass: unsupported sweep count");
+    }
+    int sweeps_warp2d(mg_ctx *c, int L, R *&cur, R *&oth, const R *f, const Coef<A> &cf, int n,
+                      const R *Vp, R *Rout)
+    {
+        const int tb = c->tb2;
+        int np = (n + tb - 1) / tb, base = n / np, extra = n % np;
+        for (int i = 0; i < np; ++i) {
+            int S = base + (i < extra ? 1 : 0);
+            int rc = warp2d_pass(c, L, S, i == 0 && Vp, i == np - 1 && Rout, oth, cur, f, Vp, Rout, cf);
+            if (rc) return rc;
+            R *t = cur; cur = oth; oth = t;
+        }
+        return MG_OK;
+    }
+
     int sweeps(mg_ctx *c, int lv, R *&cur, R *&oth, const R *f, double h, int n, const R *Vp, R *Rout)
     {
         const int L = 1 << lv;
         const Coef<A> cf = make_coef<A>(DIM, h);
-        if (DIM == 3 && c->tb >= 1 && L >= c->stream_min_L && n >= 1 && !(Vp && Rout && n <= c->tb))
-            return sweeps_stream3d(c, L, cur, oth, f, cf, n, Vp, Rout);
+        if constexpr (DIM == 2) {
+            if (c->tb2 >= 1 && L >= c->warp2d_min_L && n >= 1 && !(Vp && Rout && n <= c->tb2))
+                return sweeps_warp2d(c, L, cur, oth, f, cf, n, Vp, Rout);
+        }
+        if constexpr (DIM == 3) {
+            if (c->tb >= 1 && L >= c->stream_min_L && n >= 1 && !(Vp && Rout && n <= c->tb))
+                return sweeps_stream3d(c, L, cur, oth, f, cf, n, Vp, Rout);
+        }
         dim3 b = block_for(L), g = grid_for(DIM, L, b);
         for (int s = 0; s < n; ++s) {
             c->prof_begin(s == 0 && Vp ? MG_K_SWEEP_PROLONG : MG_K_SWEEP, L, 1);
@@ -521,6 +581,7 @@ inline int mg_ctx::init(int dim_, int size_, int real_kind_, int smooth_, int de
     if (nlevels > mg::MAX_LEVELS) return fail(MG_EINVAL, "too many levels");
     N = level_elems(nlevels - 1);
     small_L = dim == 3 ? 16 : 64;
+    tb2 = real_kind == MG_REAL_F32 ? 7 : 4;  // double arithmetic: 8 pipeline stages would spill
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0)

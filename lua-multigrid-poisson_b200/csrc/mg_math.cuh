@@ -93,6 +93,32 @@ template <int DIM, typename A> __device__ __forceinline__ A jacobi_point(A S, A 
     return div_adiag<DIM, A>(jacobi_num<A>(S, f, c), c);
 }
 
+// The same division for a group of N numerators with ONE branch for the whole group: the
+// Markstein sequence for everybody unless some numerator is in the guarded tiny range, in
+// which case everybody takes IEEE division (identical results outside that range).
+template <int DIM, typename A, int N> __device__ __forceinline__ void div_adiag_group(const A *n, A *q, const Coef<A> &c)
+{
+    if (DIM == 2) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) q[i] = Ar<A>::mul(n[i], c.cneg);
+    } else {
+        bool slow = false;
+#pragma unroll
+        for (int i = 0; i < N; ++i) slow |= (Ar<A>::abs(n[i]) < Ar<A>::tiny()) & (n[i] != (A)0);
+        if (!slow) {
+#pragma unroll
+            for (int i = 0; i < N; ++i) {
+                A q1 = Ar<A>::mul(n[i], c.yneg);
+                A r = Ar<A>::fma(c.nadiag, q1, n[i]);
+                q[i] = Ar<A>::fma(r, c.yneg, q1);
+            }
+        } else {
+#pragma unroll 1
+            for (int i = 0; i < N; ++i) q[i] = Ar<A>::div(n[i], c.adiag);
+        }
+    }
+}
+
 // r = f - (S/h^2 + adiag*u): product and sum separately rounded (cpu-raw.lua:55-56)
 template <typename A> __device__ __forceinline__ A residual_point(A S, A f, A u, const Coef<A> &c)
 {

@@ -136,14 +136,16 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, Stream3DArgs<R> a, Coef<
     typedef typename Vec<R>::T VT;
     constexpr int VX = C::VX, NST = C::NST, H = C::H, NP = 2 * VX;
 
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    // layout: [NSLOT input slots][NRING*2 stage slots][NSLOT mbarriers]
-    unsigned char *sbase = (unsigned char *)(((uintptr_t)smem_raw + 127) & ~(uintptr_t)127);
-    auto in_slot = [&](int k) -> R * { return (R *)(sbase + (size_t)k * C::SLOT_BYTES); };
-    auto ring_slot = [&](int s, int par) -> R * {
-        return (R *)(sbase + (size_t)(C::NSLOT + 2 * s + par) * C::SLOT_BYTES);
-    };
-    uint64_t *mbar = (uint64_t *)(sbase + (size_t)(C::NSLOT + 2 * C::NRING) * C::SLOT_BYTES);
+    // layout: [NSLOT input slots][NRING*2 stage slots][NSLOT mbarriers]; the dynamic shared
+    // window starts at offset 0 of the CTA's shared memory (no static __shared__ in this
+    // kernel), so every slot is 128-byte aligned as TMA requires. Pointers are derived from
+    // the __shared__ array itself so that loads/stores compile to LDS/STS.
+    extern __shared__ __align__(1024) unsigned char smem_raw[];
+    constexpr int SLOT_ELEMS = C::SLOT_BYTES / (int)sizeof(R);
+    R *const sm = reinterpret_cast<R *>(smem_raw);
+    auto in_slot = [&](int k) -> R * { return sm + k * SLOT_ELEMS; };
+    auto ring_slot = [&](int s, int par) -> R * { return sm + (C::NSLOT + 2 * s + par) * SLOT_ELEMS; };
+    uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)(C::NSLOT + 2 * C::NRING) * C::SLOT_BYTES);
 
     const int tid = threadIdx.x;
     const bool worker = tid < C::NT;
@@ -221,6 +223,9 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, Stream3DArgs<R> a, Coef<
     for (int s = 0; s < NST; ++s)
 #pragma unroll
         for (int i = 0; i < NP; ++i) { acc[s][i] = (A)0; prev[s][i] = (A)0; }
+    R fpre[NP];   // f of the plane stage 1 completes at the NEXT step, fetched one step ahead
+#pragma unroll
+    for (int i = 0; i < NP; ++i) fpre[i] = (R)0;
     A rpart[VX];  // RES: restriction partial sums of the even plane (VX/2 coarse cells x ... kept per pair)
 #pragma unroll
     for (int i = 0; i < VX; ++i) rpart[i] = (A)0;
@@ -258,12 +263,17 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, Stream3DArgs<R> a, Coef<
             const bool is_res = RES && s == NST;
             const bool last_jacobi = s == S;
 
-            // f for the emitted plane (issued early; consumed after the shared-memory work)
+            // f of the emitted plane. Stage 1 touches each f plane first (an HBM/L2 miss), so its
+            // values were fetched one step ahead into fpre; later stages re-read lines that
+            // are already in L1/L2.
             R fv[NP];
             const bool pin = p >= 0 && p < L;
 #pragma unroll
             for (int i = 0; i < NP; ++i) fv[i] = (R)0;
-            if (emit && pin) {
+            if (sidx == 0) {
+#pragma unroll
+                for (int i = 0; i < NP; ++i) fv[i] = fpre[i];
+            } else if (emit && pin) {
                 if (in0) Vec<R>::unpack(*(const VT *)(a.f + g0 + sLL * (size_t)p), fv);
                 if (in1) Vec<R>::unpack(*(const VT *)(a.f + g0 + sL + sLL * (size_t)p), fv + VX);
             }
@@ -275,36 +285,39 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, Stream3DArgs<R> a, Coef<
             Vec<R>::unpack(*(const VT *)(in + offD), dn);
             const R l0 = in[off0 + dl], l1 = in[off1 + dl], r0 = in[off0 + dr], r1 = in[off1 + dr];
 
-            R outv[NP];
+            A tot[NP], o[NP];
 #pragma unroll
             for (int i = 0; i < VX; ++i) {
-                // row 0 of the unit
-                {
+                {   // row 0 of the unit
                     const A xl = (A)(i == 0 ? l0 : c0[i - 1]), xr = (A)(i == VX - 1 ? r0 : c0[i + 1]);
                     const A yl = (A)up[i], yr = (A)c1[i], c = (A)c0[i];
                     const A part = Ar<A>::add(Ar<A>::add(Ar<A>::add(xl, xr), yl), yr);
-                    const A tot = Ar<A>::add(acc[sidx][i], c);                 // pending plane gets its z+1
-                    const A f_ = (A)fv[i];
-                    A o = is_res ? residual_point<A>(tot, f_, prev[sidx][i], cf) : jacobi_point<3, A>(tot, f_, cf);
-                    outv[i] = (in0 && pin) ? (R)o : (R)0;
-                    acc[sidx][i] = Ar<A>::add(part, prev[sidx][i]);           // this plane gets its z-1
+                    tot[i] = Ar<A>::add(acc[sidx][i], c);                      // pending plane gets its z+1
+                    if (is_res) o[i] = residual_point<A>(tot[i], (A)fv[i], prev[sidx][i], cf);
+                    acc[sidx][i] = Ar<A>::add(part, prev[sidx][i]);            // this plane gets its z-1
                     prev[sidx][i] = c;
                 }
-                // row 1 of the unit
-                {
+                {   // row 1 of the unit
                     const int j = VX + i;
                     const A xl = (A)(i == 0 ? l1 : c1[i - 1]), xr = (A)(i == VX - 1 ? r1 : c1[i + 1]);
                     const A yl = (A)c0[i], yr = (A)dn[i], c = (A)c1[i];
                     const A part = Ar<A>::add(Ar<A>::add(Ar<A>::add(xl, xr), yl), yr);
-                    const A tot = Ar<A>::add(acc[sidx][j], c);
-                    const A f_ = (A)fv[j];
-                    A o = is_res ? residual_point<A>(tot, f_, prev[sidx][j], cf) : jacobi_point<3, A>(tot, f_, cf);
-                    outv[j] = (in1 && pin) ? (R)o : (R)0;
+                    tot[j] = Ar<A>::add(acc[sidx][j], c);
+                    if (is_res) o[j] = residual_point<A>(tot[j], (A)fv[j], prev[sidx][j], cf);
                     acc[sidx][j] = Ar<A>::add(part, prev[sidx][j]);
                     prev[sidx][j] = c;
                 }
             }
             if (!emit) continue;
+            if (!is_res) {
+                A num[NP];
+#pragma unroll
+                for (int i = 0; i < NP; ++i) num[i] = jacobi_num<A>(tot[i], (A)fv[i], cf);
+                div_adiag_group<3, A, NP>(num, o, cf);
+            }
+            R outv[NP];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) outv[i] = (((i < VX) ? in0 : in1) && pin) ? (R)o[i] : (R)0;
 
             if (!is_res) {
                 if (s < NST) {  // feed the next stage
@@ -340,6 +353,16 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, Stream3DArgs<R> a, Coef<
             }
         }
 
+        // prefetch f for stage 1's next emission: plane zb + (t + 1) - 1
+        {
+            const int pn = zb + t;
+#pragma unroll
+            for (int i = 0; i < NP; ++i) fpre[i] = (R)0;
+            if (t + 1 >= 2 && pn >= 0 && pn < L) {
+                if (in0) Vec<R>::unpack(*(const VT *)(a.f + g0 + sLL * (size_t)pn), fpre);
+                if (in1) Vec<R>::unpack(*(const VT *)(a.f + g0 + sL + sLL * (size_t)pn), fpre + VX);
+            }
+        }
         // (PRO) prepare next step's input plane in place
         if (PRO && t + 1 < nin) {
             mbar_wait(&mbar[(t + 1) % C::NSLOT], (uint32_t)(((t + 1) / C::NSLOT) & 1));

@@ -68,7 +68,8 @@ int mg_set_stream(mg_ctx *ctx, void *cuda_stream);   /* borrow a cudaStream_t (N
  * Negative = keep. None of these changes a single bit of any result. */
 int mg_set_tuning(mg_ctx *ctx, int tb, int small_L, int use_graph);
 /* named integer options: "tb", "small_L", "graph", "stream_min_L" (smallest level width
- * given to the streaming smoother), "tz" (planes per CTA of the streaming smoother; 0 = auto) */
+ * given to the streaming smoother), "tz" (planes per CTA of the streaming smoother; 0 = auto), "tb2" (2-D: sweeps per pass of the
+ * warp-streaming smoother, 0..7), "warp2d_min_L", "ty" (2-D: rows per warp work item) */
 int mg_set_option(mg_ctx *ctx, const char *name, int value);
 int mg_get_info(mg_ctx *ctx, int *dim, int *size, int *real_kind, int *smooth, int *nlevels,
                 uint64_t *arena_bytes);
