@@ -227,6 +227,9 @@ def run_ours(args):
     elem = 8 if args.real == "double" else 4
     s = pkg.MultigridCUDA(args.size, args.real, dim=args.dim, device=local, out=False)
     s.set_tuning(tb=args.tb, small_L=args.small_L, use_graph=0 if args.no_graph else 1)
+    for kv in args.opt:
+        k, v = kv.split("=")
+        s.set_option(k, int(v))
     stream = torch.cuda.Stream()
     s.set_stream(stream.cuda_stream)
     lib, h = pkg.lib(), s._h
@@ -343,7 +346,7 @@ def run_ours(args):
             "scaling": "weak", "vs_baseline": None, "dtype": dtype_name(args.real), "data": "synthetic",
             "config": workload_config(args, world), "roofline": roofline, "vcycle": vcycle,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
-            "tuning": {"tb": args.tb, "small_L": args.small_L, "graph": not args.no_graph},
+            "tuning": {"tb": args.tb, "small_L": args.small_L, "graph": not args.no_graph, "opt": args.opt},
             "finite": finite,
         }
         if world > 1:
@@ -367,6 +370,7 @@ def main():
     ap.add_argument("--small-L", dest="small_L", type=int, default=-1)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--opt", action="append", default=[], help="library option name=value (mg_set_option)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -297,11 +297,13 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
     template <int S, bool PRO, bool RES>
     int launch_stream3d(mg_ctx *c, int L, R *dst, const R *src, const R *f, const R *Vp, R *Rout, const Coef<A> &cf)
     {
-        constexpr int TX = 64, TY = 32;
+        // in-plane tile: 64 x 32 for 4-byte reals, 32 x 32 for 8-byte reals (shared-memory budget)
+        constexpr int TX = sizeof(R) == 4 ? 64 : 32, TY = 32;
         typedef Stream3DCfg<R, S, RES, TX, TY> C;
-        const CUtensorMap *map = nullptr;
+        const CUtensorMap *map = nullptr, *fmap = nullptr;
         int rc = c->tensor_map(src, L, C::WX, C::WY, &map);
         if (rc) return rc;
+        if ((rc = c->tensor_map(f, L, C::WX, C::WY, &fmap))) return rc;
         auto kern = k_stream3d<R, A, S, PRO, RES, TX, TY>;
         MG_CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         // planes per CTA: minimise waves x steps-per-CTA on 148 SMs (one CTA per SM)
@@ -318,9 +320,9 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         if (TZ > L) TZ = L;
         TZ &= ~1;
         dim3 grid((L + TX - 1) / TX, (L + TY - 1) / TY, (L + TZ - 1) / TZ);
-        Stream3DArgs<R> a{dst, f, Vp, Rout, L, TZ};
+        Stream3DArgs<R> a{dst, Vp, Rout, L, TZ};
         c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : (RES ? MG_K_SWEEP_RESTRICT : MG_K_SWEEP), L, S);
-        kern<<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(*map, a, cf);
+        kern<<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(*map, *fmap, a, cf);
         c->prof_end();
         MG_LAUNCH_CHECK(c);
         return MG_OK;

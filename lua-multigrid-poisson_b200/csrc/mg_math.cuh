@@ -113,8 +113,8 @@ template <int DIM, typename A, int N> __device__ __forceinline__ void div_adiag_
                 q[i] = Ar<A>::fma(r, c.yneg, q1);
             }
         } else {
-#pragma unroll 1
-            for (int i = 0; i < N; ++i) q[i] = Ar<A>::div(n[i], c.adiag);
+#pragma unroll
+            for (int i = 0; i < N; ++i) q[i] = Ar<A>::div(n[i], c.adiag);  // unrolled: keeps n/q in registers
         }
     }
 }

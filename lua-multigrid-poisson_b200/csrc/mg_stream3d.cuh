@@ -30,6 +30,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include <type_traits>
+
 #include "mg_math.cuh"
 
 namespace mg {
@@ -112,16 +114,19 @@ template <typename R, int S, bool RES, int TX, int TY> struct Stream3DCfg {
     static constexpr int PLANE = WX * WY;
     static constexpr int PLANE_BYTES = PLANE * (int)sizeof(R);
     static constexpr int SLOT_BYTES = (PLANE_BYTES + 127) / 128 * 128;
-    static constexpr int NSLOT = 4;
-    static constexpr int NRING = NST - 1;  // intermediate stage outputs, double buffered
-    static constexpr int SMEM_BYTES = NSLOT * SLOT_BYTES + NRING * 2 * SLOT_BYTES + NSLOT * 8 + 128;
+    static constexpr int SLOT_ELEMS = SLOT_BYTES / (int)sizeof(R);
+    static constexpr int NSLOT = 3;         // source-plane ring (TMA prefetch distance NSLOT-1 steps)
+    static constexpr int NRING = NST - 1;   // intermediate stage outputs, double buffered
+    static constexpr int NF = 2 * NST + 1;  // f-plane ring: a plane lives 2*NST-1 steps, fetched 2 ahead
+    static constexpr int NSLOTS_TOTAL = NSLOT + 2 * NRING + NF;
+    static constexpr int SMEM_BYTES = NSLOTS_TOTAL * SLOT_BYTES + (NSLOT + NF) * 8;
     static_assert(TX % VX == 0 && TY % 2 == 0 && WY % 2 == 0, "tile shape");
     static_assert(NTHREADS <= 1024, "too many threads");
+    static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
 };
 
 template <typename R> struct Stream3DArgs {
     R *dst;           // u after S sweeps
-    const R *f;       // right-hand side of this level
     const R *Vp;      // PRO: coarse correction Vs[L/2]
     R *Rout;          // RES: Rs[L/2]
     int L;            // level width
@@ -130,22 +135,24 @@ template <typename R> struct Stream3DArgs {
 
 template <typename R, typename A, int S, bool PRO, bool RES, int TX, int TY>
 __global__ void __launch_bounds__((Stream3DCfg<R, S, RES, TX, TY>::NTHREADS), 1)
-k_stream3d(const __grid_constant__ CUtensorMap src_map, Stream3DArgs<R> a, Coef<A> cf)
+k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap f_map,
+           Stream3DArgs<R> a, Coef<A> cf)
 {
     typedef Stream3DCfg<R, S, RES, TX, TY> C;
     typedef typename Vec<R>::T VT;
-    constexpr int VX = C::VX, NST = C::NST, H = C::H, NP = 2 * VX;
+    constexpr int VX = C::VX, NST = C::NST, H = C::H, NP = 2 * VX, NSLOT = C::NSLOT, NF = C::NF;
 
-    // layout: [NSLOT input slots][NRING*2 stage slots][NSLOT mbarriers]; the dynamic shared
-    // window starts at offset 0 of the CTA's shared memory (no static __shared__ in this
-    // kernel), so every slot is 128-byte aligned as TMA requires. Pointers are derived from
-    // the __shared__ array itself so that loads/stores compile to LDS/STS.
+    // layout: [NSLOT source slots][NRING*2 stage slots][NF f slots][mbarriers]. The dynamic
+    // shared window starts at offset 0 of the CTA's shared memory (no static __shared__ in
+    // this kernel), so every slot is 128-byte aligned as TMA requires. Pointers are derived
+    // from the __shared__ array itself so that accesses compile to LDS/STS.
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    constexpr int SLOT_ELEMS = C::SLOT_BYTES / (int)sizeof(R);
     R *const sm = reinterpret_cast<R *>(smem_raw);
-    auto in_slot = [&](int k) -> R * { return sm + k * SLOT_ELEMS; };
-    auto ring_slot = [&](int s, int par) -> R * { return sm + (C::NSLOT + 2 * s + par) * SLOT_ELEMS; };
-    uint64_t *const mbar = reinterpret_cast<uint64_t *>(smem_raw + (size_t)(C::NSLOT + 2 * C::NRING) * C::SLOT_BYTES);
+    auto in_slot = [&](int k) -> R * { return sm + k * C::SLOT_ELEMS; };
+    auto ring_slot = [&](int s, int par) -> R * { return sm + (NSLOT + 2 * s + par) * C::SLOT_ELEMS; };
+    auto f_slot = [&](int k) -> R * { return sm + (NSLOT + 2 * C::NRING + k) * C::SLOT_ELEMS; };
+    uint64_t *const mbar_u = reinterpret_cast<uint64_t *>(smem_raw + (size_t)C::NSLOTS_TOTAL * C::SLOT_BYTES);
+    uint64_t *const mbar_f = mbar_u + NSLOT;
 
     const int tid = threadIdx.x;
     const bool worker = tid < C::NT;
@@ -175,38 +182,45 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, Stream3DArgs<R> a, Coef<
     const bool st0 = in0 && xint && (2 * uy >= C::HY) && (2 * uy < C::HY + TY);
     const bool st1 = in1 && xint && (2 * uy + 1 >= C::HY) && (2 * uy + 1 < C::HY + TY);
     const size_t sL = (size_t)L, sLL = sL * sL;
-    const size_t g0 = (size_t)gx0 + sL * (size_t)gy0;              // only used when in-domain
+    R *const dst0 = a.dst + ((size_t)gx0 + sL * (size_t)gy0);      // dereferenced only when in-domain
+    // the whole (tile + halo) footprint lies inside the grid in x and y: no in-plane masking
+    const bool cta_inner = (x0 - C::HX >= 0) && (x0 + TX + C::HX <= L) && (y0 - C::HY >= 0) && (y0 + TY + C::HY <= L);
 
     if (tid == 0) {
 #pragma unroll
-        for (int k = 0; k < C::NSLOT; ++k) mbar_init(&mbar[k], 1);
+        for (int k = 0; k < NSLOT; ++k) mbar_init(&mbar_u[k], 1);
+#pragma unroll
+        for (int k = 0; k < NF; ++k) mbar_init(&mbar_f[k], 1);
         mbar_fence_init();
     }
     __syncthreads();
     if (tid == 0) {
 #pragma unroll
-        for (int k = 0; k < C::NSLOT - 1; ++k)
+        for (int k = 0; k < NSLOT - 1; ++k)
             if (k < nin) {
-                mbar_expect_tx(&mbar[k], C::PLANE_BYTES);
-                tma_load_3d(in_slot(k), &src_map, x0 - C::HX, y0 - C::HY, zb + k, &mbar[k]);
+                mbar_expect_tx(&mbar_u[k], C::PLANE_BYTES);
+                tma_load_3d(in_slot(k), &src_map, x0 - C::HX, y0 - C::HY, zb + k, &mbar_u[k]);
             }
+        // f plane j (global z = zb + j) is first needed at step j + 1 (stage 1) and last at step
+        // j + 2*NST - 1 (stage NST); it is fetched at step j - 1, when the slot's previous tenant
+        // j - NF retired (step j - 2). Plane 0 is never used but is fetched here so that every
+        // slot sees its planes in order (uniform mbarrier phases).
+        mbar_expect_tx(&mbar_f[0], C::PLANE_BYTES);
+        tma_load_3d(f_slot(0), &f_map, x0 - C::HX, y0 - C::HY, zb, &mbar_f[0]);
     }
 
-    // PRO: add prolong(V) to the own points of an arrived input slot, in place
-    auto fixup = [&](int t) {
+    // PRO: add prolong(V) to the own points of an arrived source slot, in place
+    auto fixup = [&](int t, int slot) {
         if (!PRO || !worker) return;
         const int p = zb + t;
         if (p < 0 || p >= L) return;                               // plane outside the grid stays 0
-        R *sl = in_slot(t % C::NSLOT);
+        R *sl = in_slot(slot);
         const int L2 = L >> 1;
-        const size_t cbase = (size_t)(gx0 >> 1) + (size_t)L2 * ((size_t)(gy0 >> 1) + (size_t)L2 * (p >> 1));
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const bool in = r == 0 ? in0 : in1;
             if (!in) continue;
-            // rows gy0 and gy0+1 share a coarse row only if gy0 is even
             const size_t crow = (size_t)(gx0 >> 1) + (size_t)L2 * ((size_t)((gy0 + r) >> 1) + (size_t)L2 * (p >> 1));
-            (void)cbase;
             R u[VX];
             Vec<R>::unpack(*(const VT *)(sl + (r == 0 ? off0 : off1)), u);
 #pragma unroll
@@ -223,59 +237,73 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, Stream3DArgs<R> a, Coef<
     for (int s = 0; s < NST; ++s)
 #pragma unroll
         for (int i = 0; i < NP; ++i) { acc[s][i] = (A)0; prev[s][i] = (A)0; }
-    R fpre[NP];   // f of the plane stage 1 completes at the NEXT step, fetched one step ahead
+    A rpart[VX / 2 > 0 ? VX / 2 : 1];  // RES: restriction partial sums of the even plane
 #pragma unroll
-    for (int i = 0; i < NP; ++i) fpre[i] = (R)0;
-    A rpart[VX];  // RES: restriction partial sums of the even plane (VX/2 coarse cells x ... kept per pair)
-#pragma unroll
-    for (int i = 0; i < VX; ++i) rpart[i] = (A)0;
+    for (int i = 0; i < VX / 2; ++i) rpart[i] = (A)0;
 
     if (PRO) {
-        mbar_wait(&mbar[0], 0);
-        fixup(0);
+        mbar_wait(&mbar_u[0], 0);
+        fixup(0, 0);
         __syncthreads();
     }
 
-    for (int t = 0; t < T; ++t) {
-        // (1) refill the slot consumed at step t-1 (all threads passed the barrier ending it)
+    // ring cursors, advanced once per step (no integer division in the loop)
+    int su = 0, pu = 0;        // source slot of step t = t % NSLOT, and its mbarrier parity
+    int sf = NF - 1, pf = 1;   // slot/parity of f plane j = t - 1 (stage 1's plane); j = -1 at t = 0
+    // (sf, pf) track j = t - 1: j = -1 -> slot NF-1 of "phase -1" (parity 1); becomes (0, 0) at t = 1
+
+    // One pipeline step. STEADY: every stage is active, emits, and every emitted plane is inside
+    // the grid and (for the last Jacobi stage) inside [z0, z1): no per-stage predicates.
+    // MASKED: the tile footprint crosses the grid boundary in x or y.
+    auto step = [&](auto steady_tag, auto masked_tag, const int t) {
+        constexpr bool ST = decltype(steady_tag)::value, MK = decltype(masked_tag)::value;
+        // (1) refill: the source slot consumed at step t-1 and the f slot retired at step t-1
         if (tid == 0) {
-            const int k = t + C::NSLOT - 1;
+            const int k = t + NSLOT - 1;
             if (k < nin) {
+                const int ks = su == 0 ? NSLOT - 1 : su - 1;  // (t + NSLOT - 1) % NSLOT
                 fence_proxy_async_smem();
-                mbar_expect_tx(&mbar[k % C::NSLOT], C::PLANE_BYTES);
-                tma_load_3d(in_slot(k % C::NSLOT), &src_map, x0 - C::HX, y0 - C::HY, zb + k, &mbar[k % C::NSLOT]);
+                mbar_expect_tx(&mbar_u[ks], C::PLANE_BYTES);
+                tma_load_3d(in_slot(ks), &src_map, x0 - C::HX, y0 - C::HY, zb + k, &mbar_u[ks]);
+            }
+            const int j = t + 1;                              // f plane stage 1 needs at step t + 2
+            if (j <= nin - 2) {
+                int ksf = sf + 2; if (ksf >= NF) ksf -= NF;   // (t + 1) % NF  (sf = (t - 1) % NF)
+                mbar_expect_tx(&mbar_f[ksf], C::PLANE_BYTES);
+                tma_load_3d(f_slot(ksf), &f_map, x0 - C::HX, y0 - C::HY, zb + j, &mbar_f[ksf]);
             }
         }
-        // (2) input plane of this step (PRO: it was awaited and fixed up during step t-1)
+        // (2) source plane of this step (PRO: it was awaited and fixed up during step t-1)
         if (!PRO) {
-            if (t < nin) mbar_wait(&mbar[t % C::NSLOT], (uint32_t)((t / C::NSLOT) & 1));
+            if (ST || t < nin) mbar_wait(&mbar_u[su], (uint32_t)pu);
         }
-
-        // (3) the pipeline stages; stage s = sidx+1
+        // (3) the pipeline stages; stage s = sidx + 1
 #pragma unroll
         for (int sidx = 0; sidx < NST; ++sidx) {
             const int s = sidx + 1;
-            const bool active = (t >= 3 * sidx) && (t <= nin + s - 2);
-            if (!active || !worker) continue;
-            const bool emit = t >= 3 * s - 1;
+            if (!ST) {
+                const bool active = (t >= 3 * sidx) && (t <= nin + s - 2);
+                if (!active) continue;
+            }
+            if (!worker) continue;
+            const bool emit = ST ? true : (t >= 3 * s - 1);
             const int p = zb + t - 2 * sidx - 1;                   // plane emitted (q - 1)
-            const R *in = sidx == 0 ? in_slot(t % C::NSLOT) : ring_slot(sidx - 1, (t - 1) & 1);
+            const R *in = sidx == 0 ? in_slot(su) : ring_slot(sidx - 1, (t - 1) & 1);
             const bool is_res = RES && s == NST;
             const bool last_jacobi = s == S;
+            const bool pin = ST ? true : (p >= 0 && p < L);
 
-            // f of the emitted plane. Stage 1 touches each f plane first (an HBM/L2 miss), so its
-            // values were fetched one step ahead into fpre; later stages re-read lines that
-            // are already in L1/L2.
+            // f of the emitted plane, from the f ring (TMA zero fill covers everything outside the grid)
             R fv[NP];
-            const bool pin = p >= 0 && p < L;
+            if (emit) {
+                int kf = sf - 2 * sidx; if (kf < 0) kf += NF;      // (t - 1 - 2*sidx) % NF
+                if (sidx == 0) mbar_wait(&mbar_f[kf], (uint32_t)pf);
+                const R *fs = f_slot(kf);
+                Vec<R>::unpack(*(const VT *)(fs + off0), fv);
+                Vec<R>::unpack(*(const VT *)(fs + off1), fv + VX);
+            } else {
 #pragma unroll
-            for (int i = 0; i < NP; ++i) fv[i] = (R)0;
-            if (sidx == 0) {
-#pragma unroll
-                for (int i = 0; i < NP; ++i) fv[i] = fpre[i];
-            } else if (emit && pin) {
-                if (in0) Vec<R>::unpack(*(const VT *)(a.f + g0 + sLL * (size_t)p), fv);
-                if (in1) Vec<R>::unpack(*(const VT *)(a.f + g0 + sL + sLL * (size_t)p), fv + VX);
+                for (int i = 0; i < NP; ++i) fv[i] = (R)0;
             }
 
             R c0[VX], c1[VX], up[VX], dn[VX];
@@ -317,7 +345,10 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, Stream3DArgs<R> a, Coef<
             }
             R outv[NP];
 #pragma unroll
-            for (int i = 0; i < NP; ++i) outv[i] = (((i < VX) ? in0 : in1) && pin) ? (R)o[i] : (R)0;
+            for (int i = 0; i < NP; ++i) {
+                const bool keep = MK ? (((i < VX) ? in0 : in1) && pin) : pin;
+                outv[i] = (ST && !MK) ? (R)o[i] : (keep ? (R)o[i] : (R)0);
+            }
 
             if (!is_res) {
                 if (s < NST) {  // feed the next stage
@@ -325,11 +356,12 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, Stream3DArgs<R> a, Coef<
                     *(VT *)(out + off0) = Vec<R>::pack(outv);
                     *(VT *)(out + off1) = Vec<R>::pack(outv + VX);
                 }
-                if (last_jacobi && p >= z0 && p < z1) {
-                    if (st0) *(VT *)(a.dst + g0 + sLL * (size_t)p) = Vec<R>::pack(outv);
-                    if (st1) *(VT *)(a.dst + g0 + sL + sLL * (size_t)p) = Vec<R>::pack(outv + VX);
+                if (last_jacobi && (ST || (p >= z0 && p < z1))) {
+                    R *d = dst0 + sLL * (size_t)p;
+                    if (st0) *(VT *)d = Vec<R>::pack(outv);
+                    if (st1) *(VT *)(d + sL) = Vec<R>::pack(outv + VX);
                 }
-            } else if (p >= z0 && p < z1 && st0 && st1) {
+            } else if ((ST || (p >= z0 && p < z1)) && st0 && st1) {
                 // restriction: children in the order i fastest, then j, then k (SURVEY 8(a'))
                 const int L2 = L >> 1;
                 if ((p & 1) == 0) {
@@ -353,22 +385,28 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, Stream3DArgs<R> a, Coef<
             }
         }
 
-        // prefetch f for stage 1's next emission: plane zb + (t + 1) - 1
-        {
-            const int pn = zb + t;
-#pragma unroll
-            for (int i = 0; i < NP; ++i) fpre[i] = (R)0;
-            if (t + 1 >= 2 && pn >= 0 && pn < L) {
-                if (in0) Vec<R>::unpack(*(const VT *)(a.f + g0 + sLL * (size_t)pn), fpre);
-                if (in1) Vec<R>::unpack(*(const VT *)(a.f + g0 + sL + sLL * (size_t)pn), fpre + VX);
-            }
-        }
-        // (PRO) prepare next step's input plane in place
+        // (PRO) prepare next step's source plane in place
         if (PRO && t + 1 < nin) {
-            mbar_wait(&mbar[(t + 1) % C::NSLOT], (uint32_t)(((t + 1) / C::NSLOT) & 1));
-            fixup(t + 1);
+            const int sn = su + 1 == NSLOT ? 0 : su + 1;
+            mbar_wait(&mbar_u[sn], (uint32_t)(sn == 0 ? pu ^ 1 : pu));
+            fixup(t + 1, sn);
         }
         __syncthreads();
+        // advance the ring cursors
+        if (++su == NSLOT) { su = 0; pu ^= 1; }
+        if (++sf == NF) { sf = 0; pf ^= 1; }
+    };
+
+    // steady range: all stages active and emitting, every emitted plane inside the grid
+    const int t_lo = 3 * NST - 1;
+    const int t_hi = min(nin - 1, L - zb);   // stage 1 emits plane zb + t - 1 <= L - 1
+    for (int t = 0; t < T; ++t) {
+        if (t >= t_lo && t <= t_hi && zb + t - 2 * NST + 1 >= 0) {
+            if (cta_inner) step(std::true_type{}, std::false_type{}, t);
+            else step(std::true_type{}, std::true_type{}, t);
+        } else {
+            step(std::false_type{}, std::true_type{}, t);
+        }
     }
 }
 

@@ -179,3 +179,57 @@ def main():
 
 if __name__ == "__main__":
     main()
+
+
+def check_rings(NST, TZ, NSLOT=3):
+    """Slot/phase bookkeeping of the source ring and the f ring exactly as k_stream3d does it
+    (cursors su/pu, sf/pf; issue at step t of source plane t+NSLOT-1 and f plane t+1)."""
+    H = NST
+    NF = 2 * NST + 1
+    nin, T = TZ + 2 * H, TZ + 3 * H - 1
+    uslot, uloads = [None] * NSLOT, [0] * NSLOT      # tenant plane, number of completed loads
+    fslot, floads = [None] * NF, [0] * NF
+    f_last_use = {}
+    for k in range(NSLOT - 1):
+        if k < nin:
+            uslot[k] = k; uloads[k] += 1
+    fslot[0] = 0; floads[0] += 1
+    su, pu, sf, pf = 0, 0, NF - 1, 1
+    for t in range(T):
+        k = t + NSLOT - 1
+        if k < nin:
+            ks = NSLOT - 1 if su == 0 else su - 1
+            assert ks == k % NSLOT
+            assert uslot[ks] is None or uslot[ks] <= t - 1, "source slot still in use"
+            uslot[ks] = k; uloads[ks] += 1
+        j = t + 1
+        if j <= nin - 2:
+            ksf = (sf + 2) % NF
+            assert ksf == j % NF
+            old = fslot[ksf]
+            assert old is None or f_last_use.get(old, -1) < t, ("f slot still in use", t, old)
+            fslot[ksf] = j; floads[ksf] += 1
+        if t < nin:
+            assert uslot[su] == t and (uloads[su] - 1) & 1 == pu, ("source phase", t)
+        for sidx in range(NST):
+            s = sidx + 1
+            if not (t >= 3 * sidx and t <= nin + s - 2):
+                continue
+            if t >= 3 * s - 1:
+                jj = t - 1 - 2 * sidx
+                kf = (sf - 2 * sidx) % NF
+                assert 1 <= jj <= nin - 2 and fslot[kf] == jj, ("f plane", t, s, jj, fslot[kf])
+                if sidx == 0:
+                    assert (floads[kf] - 1) & 1 == pf, ("f phase", t, jj, floads[kf], pf)
+                f_last_use[jj] = t
+        su += 1
+        if su == NSLOT:
+            su, pu = 0, pu ^ 1
+        sf += 1
+        if sf == NF:
+            sf, pf = 0, pf ^ 1
+    return True
+
+
+if __name__ == "__main__" and "--rings" in sys.argv:
+    pass
