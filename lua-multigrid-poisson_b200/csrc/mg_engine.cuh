@@ -59,6 +59,7 @@ struct mg_ctx {
     int warp2d_min_L = 128;  // 2-D: smallest level width handled by the warp-streaming smoother
     int ty_override = 0;     // 2-D: rows per warp work item (0 = cost model)
     int stream_min_L = 128;  // smallest level width handled by the streaming (TMA) smoother
+    int stream_flags = 0;    // debug switches of the streaming smoother (see Stream3DArgs::flags)
     int tz_override = 0;     // planes per CTA of the streaming smoother (0 = cost model)
     // TMA descriptors of the source fields, keyed by (pointer, level width, box x, box y)
     std::map<std::tuple<const void *, int, int, int>, CUtensorMap> tmaps;
@@ -320,7 +321,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         if (TZ > L) TZ = L;
         TZ &= ~1;
         dim3 grid((L + TX - 1) / TX, (L + TY - 1) / TY, (L + TZ - 1) / TZ);
-        Stream3DArgs<R> a{dst, Vp, Rout, L, TZ};
+        Stream3DArgs<R> a{dst, Vp, Rout, L, TZ, c->stream_flags};
         c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : (RES ? MG_K_SWEEP_RESTRICT : MG_K_SWEEP), L, S);
         kern<<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(*map, *fmap, a, cf);
         c->prof_end();

@@ -102,9 +102,16 @@ template <int DIM, typename A, int N> __device__ __forceinline__ void div_adiag_
 #pragma unroll
         for (int i = 0; i < N; ++i) q[i] = Ar<A>::mul(n[i], c.cneg);
     } else {
+        // one compare per numerator on the hot path: |n| < tiny also fires for n == 0, which is
+        // then told apart in the (rare) second look
         bool slow = false;
 #pragma unroll
-        for (int i = 0; i < N; ++i) slow |= (Ar<A>::abs(n[i]) < Ar<A>::tiny()) & (n[i] != (A)0);
+        for (int i = 0; i < N; ++i) slow |= Ar<A>::abs(n[i]) < Ar<A>::tiny();
+        if (slow) {
+            slow = false;
+#pragma unroll
+            for (int i = 0; i < N; ++i) slow |= (Ar<A>::abs(n[i]) < Ar<A>::tiny()) & (n[i] != (A)0);
+        }
         if (!slow) {
 #pragma unroll
             for (int i = 0; i < N; ++i) {

@@ -131,6 +131,7 @@ template <typename R> struct Stream3DArgs {
     R *Rout;          // RES: Rs[L/2]
     int L;            // level width
     int TZ;           // planes per CTA (even)
+    int flags;        // debug: bit 0 = never take the steady-state body, bit 1 = always mask
 };
 
 template <typename R, typename A, int S, bool PRO, bool RES, int TX, int TY>
@@ -397,15 +398,31 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         if (++sf == NF) { sf = 0; pf ^= 1; }
     };
 
-    // steady range: all stages active and emitting, every emitted plane inside the grid
+    // f plane 0 is fetched only to keep the ring's mbarrier phases uniform; it must still have
+    // landed before this CTA may exit (no TMA transfer may outlive its shared memory)
+    mbar_wait(&mbar_f[0], 0);
+
+    // Steady range: all stages active and emitting, every emitted plane inside the grid. The
+    // three phases (fill, steady, drain) are separate loops so that the per-stage registers
+    // (acc, prev) keep one assignment per loop instead of being shuffled at a merge point
+    // every step; fill and drain share one copy of the generic body.
     const int t_lo = 3 * NST - 1;
-    const int t_hi = min(nin - 1, L - zb);   // stage 1 emits plane zb + t - 1 <= L - 1
-    for (int t = 0; t < T; ++t) {
-        if (t >= t_lo && t <= t_hi && zb + t - 2 * NST + 1 >= 0) {
-            if (cta_inner) step(std::true_type{}, std::false_type{}, t);
-            else step(std::true_type{}, std::true_type{}, t);
+    int t_hi = min(nin - 1, L - zb);   // stage 1 emits plane zb + t - 1 <= L - 1
+    if ((a.flags & 1) || t_hi < t_lo) t_hi = t_lo - 1;            // no steady phase
+#pragma unroll 1
+    for (int phase = 0; phase < 3; ++phase) {
+        if (phase == 1) {
+            if (cta_inner && !(a.flags & 2)) {
+#pragma unroll 1
+                for (int t = t_lo; t <= t_hi; ++t) step(std::true_type{}, std::false_type{}, t);
+            } else {
+#pragma unroll 1
+                for (int t = t_lo; t <= t_hi; ++t) step(std::true_type{}, std::true_type{}, t);
+            }
         } else {
-            step(std::false_type{}, std::true_type{}, t);
+            const int ta = phase == 0 ? 0 : t_hi + 1, tb = phase == 0 ? min(t_lo, T) : T;
+#pragma unroll 1
+            for (int t = ta; t < tb; ++t) step(std::false_type{}, std::true_type{}, t);
         }
     }
 }

@@ -15,7 +15,7 @@ def solvers(mgp):
 
     def get(real):
         if real not in cache:
-            s = mgp.MultigridCUDA(128, real, dim=3, out=False)
+            s = mgp.MultigridCUDA(256, real, dim=3, out=False)
             s.set_option("stream_min_L", 64)
             cache[real] = s
         return cache[real]
@@ -31,7 +31,7 @@ def ref_sweeps(orc, k, u, f, h, n):
 
 
 @pytest.mark.parametrize("real", KINDS)
-@pytest.mark.parametrize("L,tz", [(64, 0), (64, 16), (128, 0), (128, 8), (128, 64)])
+@pytest.mark.parametrize("L,tz", [(64, 0), (64, 16), (128, 0), (128, 8), (128, 64), (256, 0)])
 def test_streaming_passes(solvers, orc, real, L, tz):
     s = solvers(real)
     k = orc.REAL_NAMES[real]
