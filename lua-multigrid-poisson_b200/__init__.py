@@ -29,7 +29,7 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
-LIB_PATH = os.path.join(_HERE, "libmgpoisson.so")
+LIB_PATH = os.environ.get("MGPOISSON_LIB") or os.path.join(_HERE, "libmgpoisson.so")  # same override as cuda.lua
 HEADER_PATH = os.path.join(_ROOT, "include", "mgpoisson.h")
 
 REAL_F64, REAL_F32, REAL_F32_ACC64 = 0, 1, 2

@@ -321,7 +321,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         if (TZ > L) TZ = L;
         TZ &= ~1;
         dim3 grid((L + TX - 1) / TX, (L + TY - 1) / TY, (L + TZ - 1) / TZ);
-        Stream3DArgs<R> a{dst, Vp, Rout, L, TZ, c->stream_flags};
+        Stream3DArgs<R> a{dst, Vp, Rout, L, TZ, c->stream_flags, 0, L, 0, L, 0, 0};
         c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : (RES ? MG_K_SWEEP_RESTRICT : MG_K_SWEEP), L, S);
         kern<<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(*map, *fmap, a, cf);
         c->prof_end();

@@ -32,6 +32,10 @@ template <> struct Ar<float> {
     static __device__ __forceinline__ float div(float a, float b) { return __fdiv_rn(a, b); }
     static __device__ __forceinline__ float abs(float a) { return fabsf(a); }
     static __host__ __device__ __forceinline__ float tiny() { return 1e-20f; }
+    // 2*|bits| - 1 (mod 2^32): +-0 -> 0xffffffff, otherwise monotone in |n|
+    typedef unsigned int key_t;
+    static __device__ __forceinline__ key_t guard_key(float n) { return 2u * __float_as_uint(n) - 1u; }
+    static __device__ __forceinline__ key_t guard_threshold() { return 2u * __float_as_uint(1e-20f) - 1u; }
 };
 template <> struct Ar<double> {
     static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
@@ -41,6 +45,9 @@ template <> struct Ar<double> {
     static __device__ __forceinline__ double div(double a, double b) { return __ddiv_rn(a, b); }
     static __device__ __forceinline__ double abs(double a) { return fabs(a); }
     static __host__ __device__ __forceinline__ double tiny() { return 1e-200; }
+    typedef unsigned long long key_t;
+    static __device__ __forceinline__ key_t guard_key(double n) { return 2ull * (unsigned long long)__double_as_longlong(n) - 1ull; }
+    static __device__ __forceinline__ key_t guard_threshold() { return 2ull * (unsigned long long)__double_as_longlong(1e-200) - 1ull; }
 };
 
 // Per-level coefficients, computed on the host in double and rounded to the arithmetic type
@@ -102,16 +109,17 @@ template <int DIM, typename A, int N> __device__ __forceinline__ void div_adiag_
 #pragma unroll
         for (int i = 0; i < N; ++i) q[i] = Ar<A>::mul(n[i], c.cneg);
     } else {
-        // one compare per numerator on the hot path: |n| < tiny also fires for n == 0, which is
-        // then told apart in the (rare) second look
-        bool slow = false;
+        // Hot path: one key per numerator and a min chain for the group. The key orders
+        // "tiny but non-zero" below everything else (zero maps to the largest key), so exact
+        // zeros -- ubiquitous outside the grid and before the first correction -- stay on the
+        // fast path. Fallback: IEEE division for the whole group (exact for every input).
+        typename Ar<A>::key_t m = Ar<A>::guard_key(n[0]);
 #pragma unroll
-        for (int i = 0; i < N; ++i) slow |= Ar<A>::abs(n[i]) < Ar<A>::tiny();
-        if (slow) {
-            slow = false;
-#pragma unroll
-            for (int i = 0; i < N; ++i) slow |= (Ar<A>::abs(n[i]) < Ar<A>::tiny()) & (n[i] != (A)0);
+        for (int i = 1; i < N; ++i) {
+            const typename Ar<A>::key_t k = Ar<A>::guard_key(n[i]);
+            m = k < m ? k : m;
         }
+        const bool slow = m < Ar<A>::guard_threshold();
         if (!slow) {
 #pragma unroll
             for (int i = 0; i < N; ++i) {

@@ -34,7 +34,16 @@
 
 #include "mg_math.cuh"
 
+#ifndef MG_STREAM_SHFL
+#define MG_STREAM_SHFL 0      // x-neighbours across units via warp shuffle (0: 4-byte shared loads)
+#endif
+#ifndef MG_STEADY_UNROLL
+#define MG_STEADY_UNROLL 2    // unroll factor of the steady-state step loop
+#endif
+
 namespace mg {
+
+constexpr int kSteadyUnroll = MG_STEADY_UNROLL;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -132,6 +141,12 @@ template <typename R> struct Stream3DArgs {
     int L;            // level width
     int TZ;           // planes per CTA (even)
     int flags;        // debug: bit 0 = never take the steady-state body, bit 1 = always mask
+    // slab view (multi-GPU): the arrays hold planes [0, nplanes) of which [nz_lo, nz_hi) are
+    // owned (written) by this rank; the global grid occupies local planes [zdom0, zdom1).
+    // Single GPU: nz_lo = zdom0 = 0, nz_hi = zdom1 = L, rz_off = vz_off = 0.
+    int nz_lo, nz_hi, zdom0, zdom1;
+    int rz_off;       // RES: coarse local plane = ((p - nz_lo) >> 1) + rz_off
+    int vz_off;       // PRO: coarse local plane = ((p - zdom0) >> 1) + vz_off
 };
 
 template <typename R, typename A, int S, bool PRO, bool RES, int TX, int TY>
@@ -155,12 +170,13 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     uint64_t *const mbar_u = reinterpret_cast<uint64_t *>(smem_raw + (size_t)C::NSLOTS_TOTAL * C::SLOT_BYTES);
     uint64_t *const mbar_f = mbar_u + NSLOT;
 
-    const int tid = threadIdx.x;
-    const bool worker = tid < C::NT;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const bool worker = tid < C::NT;   // the last warp's spare threads mirror unit 0 and never store
     const int ux = worker ? tid % C::UX : 0, uy = worker ? tid / C::UX : 0;
     const int L = a.L;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = blockIdx.z * a.TZ;
-    const int z1 = min(z0 + a.TZ, L);
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = a.nz_lo + blockIdx.z * a.TZ;
+    const int z1 = min(z0 + a.TZ, a.nz_hi);
+    const int zdom0 = a.zdom0, zdom1 = a.zdom1;
     const int TZ = z1 - z0;
     const int zb = z0 - H;          // plane index of input step 0
     const int nin = TZ + 2 * H;     // input planes
@@ -214,14 +230,15 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     auto fixup = [&](int t, int slot) {
         if (!PRO || !worker) return;
         const int p = zb + t;
-        if (p < 0 || p >= L) return;                               // plane outside the grid stays 0
+        if (p < zdom0 || p >= zdom1) return;                       // plane outside the grid stays 0
+        const int pc = ((p - zdom0) >> 1) + a.vz_off;              // coarse plane (local index)
         R *sl = in_slot(slot);
         const int L2 = L >> 1;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const bool in = r == 0 ? in0 : in1;
             if (!in) continue;
-            const size_t crow = (size_t)(gx0 >> 1) + (size_t)L2 * ((size_t)((gy0 + r) >> 1) + (size_t)L2 * (p >> 1));
+            const size_t crow = (size_t)(gx0 >> 1) + (size_t)L2 * ((size_t)((gy0 + r) >> 1) + (size_t)L2 * (size_t)pc);
             R u[VX];
             Vec<R>::unpack(*(const VT *)(sl + (r == 0 ? off0 : off1)), u);
 #pragma unroll
@@ -286,13 +303,12 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                 const bool active = (t >= 3 * sidx) && (t <= nin + s - 2);
                 if (!active) continue;
             }
-            if (!worker) continue;
             const bool emit = ST ? true : (t >= 3 * s - 1);
             const int p = zb + t - 2 * sidx - 1;                   // plane emitted (q - 1)
             const R *in = sidx == 0 ? in_slot(su) : ring_slot(sidx - 1, (t - 1) & 1);
             const bool is_res = RES && s == NST;
             const bool last_jacobi = s == S;
-            const bool pin = ST ? true : (p >= 0 && p < L);
+            const bool pin = ST ? true : (p >= zdom0 && p < zdom1);
 
             // f of the emitted plane, from the f ring (TMA zero fill covers everything outside the grid)
             R fv[NP];
@@ -312,7 +328,19 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
             Vec<R>::unpack(*(const VT *)(in + off1), c1);
             Vec<R>::unpack(*(const VT *)(in + offU), up);
             Vec<R>::unpack(*(const VT *)(in + offD), dn);
-            const R l0 = in[off0 + dl], l1 = in[off1 + dl], r0 = in[off0 + dr], r1 = in[off1 + dr];
+            // x-neighbours across units come from the adjacent lane (warp shuffle) instead of a
+            // 4-byte shared load at 16-byte stride (4-way bank conflict). Lanes 0 / 31 have no such
+            // lane and read shared memory; where the adjacent lane is a different row (ux = 0 or
+            // UX-1) the value is garbage, exactly in the garbage zone of the tile edge.
+            R l0, l1, r0, r1;
+            if (MG_STREAM_SHFL) {
+                l0 = __shfl_up_sync(0xffffffffu, c0[VX - 1], 1); l1 = __shfl_up_sync(0xffffffffu, c1[VX - 1], 1);
+                r0 = __shfl_down_sync(0xffffffffu, c0[0], 1); r1 = __shfl_down_sync(0xffffffffu, c1[0], 1);
+                if (lane == 0) { l0 = in[off0 + dl]; l1 = in[off1 + dl]; }
+                if (lane == 31) { r0 = in[off0 + dr]; r1 = in[off1 + dr]; }
+            } else {
+                l0 = in[off0 + dl]; l1 = in[off1 + dl]; r0 = in[off0 + dr]; r1 = in[off1 + dr];
+            }
 
             A tot[NP], o[NP];
 #pragma unroll
@@ -352,7 +380,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
             }
 
             if (!is_res) {
-                if (s < NST) {  // feed the next stage
+                if (s < NST && worker) {  // feed the next stage
                     R *out = ring_slot(sidx, t & 1);
                     *(VT *)(out + off0) = Vec<R>::pack(outv);
                     *(VT *)(out + off1) = Vec<R>::pack(outv + VX);
@@ -365,7 +393,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
             } else if ((ST || (p >= z0 && p < z1)) && st0 && st1) {
                 // restriction: children in the order i fastest, then j, then k (SURVEY 8(a'))
                 const int L2 = L >> 1;
-                if ((p & 1) == 0) {
+                if (((p - a.nz_lo) & 1) == 0) {
 #pragma unroll
                     for (int cidx = 0; cidx < VX / 2; ++cidx) {
                         A sacc = Ar<A>::add((A)outv[2 * cidx], (A)outv[2 * cidx + 1]);
@@ -373,7 +401,8 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                         rpart[cidx] = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx + 1]);
                     }
                 } else {
-                    const size_t cb = (size_t)(gx0 >> 1) + (size_t)L2 * ((size_t)(gy0 >> 1) + (size_t)L2 * (p >> 1));
+                    const size_t cb = (size_t)(gx0 >> 1) +
+                                      (size_t)L2 * ((size_t)(gy0 >> 1) + (size_t)L2 * (size_t)(((p - a.nz_lo) >> 1) + a.rz_off));
 #pragma unroll
                     for (int cidx = 0; cidx < VX / 2; ++cidx) {
                         A sacc = Ar<A>::add(rpart[cidx], (A)outv[2 * cidx]);
@@ -407,16 +436,16 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     // (acc, prev) keep one assignment per loop instead of being shuffled at a merge point
     // every step; fill and drain share one copy of the generic body.
     const int t_lo = 3 * NST - 1;
-    int t_hi = min(nin - 1, L - zb);   // stage 1 emits plane zb + t - 1 <= L - 1
+    int t_hi = min(nin - 1, zdom1 - zb);   // stage 1 emits plane zb + t - 1 <= zdom1 - 1
     if ((a.flags & 1) || t_hi < t_lo) t_hi = t_lo - 1;            // no steady phase
 #pragma unroll 1
     for (int phase = 0; phase < 3; ++phase) {
         if (phase == 1) {
             if (cta_inner && !(a.flags & 2)) {
-#pragma unroll 1
+#pragma unroll kSteadyUnroll
                 for (int t = t_lo; t <= t_hi; ++t) step(std::true_type{}, std::false_type{}, t);
             } else {
-#pragma unroll 1
+#pragma unroll kSteadyUnroll
                 for (int t = t_lo; t <= t_hi; ++t) step(std::true_type{}, std::true_type{}, t);
             }
         } else {
