@@ -146,15 +146,22 @@ uint64_t mg_launch_count(mg_ctx *ctx);
  * residual+restrict. L = level width, sweeps = Jacobi sweeps done by that launch. */
 int mg_profile_vcycle(mg_ctx *ctx, int cap, int *kind, int *L, int *sweeps, float *ms, int *n);
 
-/* ---- multi-GPU slabs (one handle per GPU). The domain is cut along the
- * slowest axis into nranks slabs; rank r owns planes [r*size/nranks, (r+1)*size/nranks).
- * Peers are attached by CUDA IPC handle (other process) or by pointer (same process). */
+/* ---- multi-GPU slabs (3-D only; the reference has no multi-device path). The grid is cut along
+ * z into nranks slabs; distributed levels carry ghost planes that are refreshed before every
+ * smoother pass; coarse levels below the threshold are replicated. Results are bit-identical to
+ * the single-GPU solver. Two transports:
+ *  mg_create_slab       one handle per process/GPU, halo planes by ncclSend/ncclRecv (libnccl is
+ *                       dlopen()ed). Rank 0 calls mg_nccl_unique_id and ships the 128 bytes to
+ *                       the other ranks by any means. mg_upload/mg_download/mg_step_host then
+ *                       move the planes THIS rank owns (size/nranks planes of size^2 elements).
+ *  mg_create_slab_local every slab in this process on one device (testing the slab schedule on
+ *                       a single GPU); the handle behaves like a single solver on the global grid. */
+int mg_nccl_unique_id(void *id, size_t bytes);
 int mg_create_slab(int dim, int size, int real_kind, int smooth, int device, int rank, int nranks,
-                   mg_ctx **out);
-int mg_slab_ipc_size(void);
-int mg_slab_export(mg_ctx *ctx, void *ipc_blob, size_t bytes);
-int mg_slab_attach(mg_ctx *ctx, int peer_rank, const void *ipc_blob, size_t bytes);
-int mg_slab_attach_local(mg_ctx *ctx, int peer_rank, mg_ctx *peer);
+                   const void *nccl_id, size_t id_bytes, mg_ctx **out);
+int mg_create_slab_local(int dim, int size, int real_kind, int smooth, int device, int nslabs, mg_ctx **out);
+int mg_slab_info(mg_ctx *ctx, int *rank, int *nranks, int *own_planes, int *ghost, uint64_t *exchanges,
+                 uint64_t *exchanged_bytes);
 /* MGPOISSON_CDEF_END */
 
 #ifdef __cplusplus

@@ -121,11 +121,10 @@ def lib():
         "mg_time_vcycles": (i, [vp, i, C.POINTER(C.c_float)]),
         "mg_launch_count": (u64, [vp]),
         "mg_profile_vcycle": (i, [vp, i, pi, pi, pi, C.POINTER(C.c_float), pi]),
-        "mg_create_slab": (i, [i, i, i, i, i, i, i, C.POINTER(vp)]),
-        "mg_slab_ipc_size": (i, []),
-        "mg_slab_export": (i, [vp, vp, sz]),
-        "mg_slab_attach": (i, [vp, i, vp, sz]),
-        "mg_slab_attach_local": (i, [vp, i, vp]),
+        "mg_nccl_unique_id": (i, [vp, sz]),
+        "mg_create_slab": (i, [i, i, i, i, i, i, i, vp, sz, C.POINTER(vp)]),
+        "mg_create_slab_local": (i, [i, i, i, i, i, i, C.POINTER(vp)]),
+        "mg_slab_info": (i, [vp, pi, pi, pi, pi, C.POINTER(u64), C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -160,7 +159,10 @@ class DeviceBuffer:
 
     @property
     def shape(self):
-        return (self.L,) * self.owner.dim
+        o = self.owner
+        if o.slab_n > 1 and self.L >= 64 and self.L // o.slab_n >= 8:   # distributed level: owned planes
+            return (self.L // o.slab_n,) + (self.L,) * (o.dim - 1)
+        return (self.L,) * o.dim
 
     @property
     def nbytes(self):
@@ -178,7 +180,7 @@ class DeviceBuffer:
 
     def upload(self, a):
         a = np.ascontiguousarray(a, dtype=self.owner.dtype)
-        if a.size != self.L ** self.owner.dim:
+        if a.size != int(np.prod(self.shape)):
             raise ValueError("size mismatch")
         self.owner._ck(lib().mg_upload(self.owner._h, self.which, self.L, _hptr(a), a.nbytes))
 
@@ -208,7 +210,12 @@ class MultigridCUDA:
     debugging = False   # cpu-raw.lua:121
     max_cycles = 2      # cpu-raw.lua:245 `for iter=1,2`
 
-    def __init__(self, size, real=None, cpuDepth=None, dim=2, device=-1, smooth=None, out=None):
+    def __init__(self, size, real=None, cpuDepth=None, dim=2, device=-1, smooth=None, out=None,
+                 local_slabs=1, slab=None):
+        """local_slabs > 1: cut the 3-D grid into that many slabs inside this process on one GPU
+        (exercises the multi-GPU schedule on a single device; the object still looks like one
+        solver on the global grid). slab = (rank, nranks, nccl_id_bytes): this process's slab of
+        a multi-process solver (see `create_distributed`); buffers then hold the owned planes."""
         self.real = real or "double"
         self.real_kind = REAL_NAMES[self.real] if isinstance(self.real, str) else int(self.real)
         self.dtype = np_dtype(self.real_kind)
@@ -217,7 +224,17 @@ class MultigridCUDA:
             self.smooth = int(smooth)
         self.out = out  # where run() prints its `#iter err` lines (None = stdout, False = silent)
         h = C.c_void_p()
-        rc = lib().mg_create(self.dim, self.size, self.real_kind, self.smooth, device, C.byref(h))
+        self.slab_rank, self.slab_n = 0, 1
+        if slab is not None:
+            self.slab_rank, self.slab_n, nid = slab
+            idbuf = C.create_string_buffer(bytes(nid), len(nid))
+            rc = lib().mg_create_slab(self.dim, self.size, self.real_kind, self.smooth, device, self.slab_rank,
+                                      self.slab_n, idbuf, len(nid), C.byref(h))
+        elif local_slabs > 1:
+            rc = lib().mg_create_slab_local(self.dim, self.size, self.real_kind, self.smooth, device,
+                                            int(local_slabs), C.byref(h))
+        else:
+            rc = lib().mg_create(self.dim, self.size, self.real_kind, self.smooth, device, C.byref(h))
         if rc != 0:
             raise MGError(f"mg_create failed ({rc}): {lib().mg_last_error(None).decode()}")
         self._h = h
@@ -264,6 +281,13 @@ class MultigridCUDA:
 
     def set_option(self, name, value):
         self._ck(lib().mg_set_option(self._h, name.encode(), int(value)))
+
+    def slab_info(self):
+        v = [C.c_int() for _ in range(4)]
+        ex, eb = C.c_uint64(), C.c_uint64()
+        self._ck(lib().mg_slab_info(self._h, *[C.byref(x) for x in v], C.byref(ex), C.byref(eb)))
+        return dict(rank=v[0].value, nranks=v[1].value, own_planes=v[2].value, ghost=v[3].value,
+                    exchanges=ex.value, exchanged_bytes=eb.value)
 
     def info(self):
         v = [C.c_int() for _ in range(5)]
@@ -423,3 +447,41 @@ class PinnedArray:
             self.array = None
             lib().mg_host_free(self._p)
             self._p = None
+
+
+def nccl_unique_id() -> bytes:
+    buf = C.create_string_buffer(128)
+    rc = lib().mg_nccl_unique_id(buf, 128)
+    if rc != 0:
+        raise MGError(f"mg_nccl_unique_id failed ({rc}): {lib().mg_last_error(None).decode()}")
+    return buf.raw
+
+
+def create_distributed(size, real="float", dim=3, smooth=None, out=False):
+    """One slab per process (torchrun: one process per GPU). torch.distributed is only the
+    plumbing that ships rank 0's NCCL unique id to the other ranks; every halo exchange,
+    all-gather and reduction afterwards is issued by libmgpoisson on its own communicator."""
+    import torch
+    import torch.distributed as dist
+    rank, world = dist.get_rank(), dist.get_world_size()
+    if world == 1:
+        return MultigridCUDA(size, real, dim=dim, smooth=smooth, out=out, device=torch.cuda.current_device())
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend() == "nccl" else torch.device("cpu")
+    t = torch.zeros(128, dtype=torch.uint8, device=dev)
+    if rank == 0:
+        t = torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8).to(dev)
+    dist.broadcast(t, 0)
+    nid = bytes(t.cpu().numpy().tobytes())
+    return MultigridCUDA(size, real, dim=dim, smooth=smooth, out=out, device=torch.cuda.current_device(),
+                         slab=(rank, world, nid))
+
+
+def slab_partition(size, nranks):
+    """Host-side description of the decomposition libmgpoisson uses (mg_slab.cuh): which level
+    widths are cut across the ranks, planes per rank, ghost depth, and the replicated levels."""
+    levels, L = [], size
+    while L >= 1:
+        d = nranks > 1 and L >= 64 and L // nranks >= 8
+        levels.append(dict(L=L, distributed=d, planes_per_rank=L // nranks if d else L, ghost=4 if d else 0))
+        L //= 2
+    return levels

@@ -134,16 +134,22 @@ int mg_get_info(mg_ctx *ctx, int *dim, int *size, int *real_kind, int *smooth, i
 int mg_init_cells(mg_ctx *ctx)
 {
     CTX_OR_FAIL(ctx);
-    int rc = ctx->eng->init_cells(ctx);
-    if (rc) return rc;
+    int rc = MG_OK;
+    if (ctx->group && !ctx->group->nccl) {
+        for (mg_ctx *m : ctx->group->m)
+            if ((rc = m->eng->init_cells(m))) return rc;
+    } else if ((rc = ctx->eng->init_cells(ctx))) {
+        return rc;
+    }
     return ctx->sync();
 }
 
 int mg_zero_corrections(mg_ctx *ctx)
 {
     CTX_OR_FAIL(ctx);
-    for (int lv = 0; lv < ctx->nlevels; ++lv)
-        if (ctx->V[lv]) MG_CK(ctx, cudaMemsetAsync(ctx->V[lv], 0, ctx->level_bytes(lv), ctx->stream));
+    for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx}))
+        for (int lv = 0; lv < m->nlevels; ++lv)
+            if (m->V[lv]) MG_CK(ctx, cudaMemsetAsync(m->V[lv], 0, m->level_bytes(lv), ctx->stream));
     return ctx->sync();
 }
 
@@ -156,24 +162,16 @@ void *mg_device_ptr(mg_ctx *ctx, int which, int level)
 int mg_upload(mg_ctx *ctx, int which, int level, const void *host, size_t bytes)
 {
     CTX_OR_FAIL(ctx);
-    size_t cap = 0;
-    if (which >= MG_BUF_ERRORBUF && ctx->ensure_debug_arena() != MG_OK) return MG_ENOMEM;
-    void *d = ctx->buffer(which, level, &cap);
-    if (!d || !host) return ctx->fail(MG_EINVAL, "mg_upload: no such buffer");
-    if (bytes > cap) return ctx->fail(MG_EINVAL, "mg_upload: too many bytes");
-    MG_CK(ctx, cudaMemcpyAsync(d, host, bytes, cudaMemcpyHostToDevice, ctx->stream));
-    return ctx->sync();
+    if (!ctx->group && (which == MG_BUF_ERRORBUF || which == MG_BUF_TMPU || which == MG_BUF_r || which == MG_BUF_v) &&
+        ctx->ensure_debug_arena() != MG_OK)
+        return MG_ENOMEM;
+    return ctx->copy_in(which, level, host, bytes);
 }
 
 int mg_download(mg_ctx *ctx, int which, int level, void *host, size_t bytes)
 {
     CTX_OR_FAIL(ctx);
-    size_t cap = 0;
-    void *d = ctx->buffer(which, level, &cap);
-    if (!d || !host) return ctx->fail(MG_EINVAL, "mg_download: buffer not materialised");
-    if (bytes > cap) return ctx->fail(MG_EINVAL, "mg_download: too many bytes");
-    MG_CK(ctx, cudaMemcpyAsync(host, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-    return ctx->sync();
+    return ctx->copy_out(which, level, host, bytes);
 }
 
 void *mg_host_alloc(size_t bytes)
@@ -232,13 +230,21 @@ int mg_step_host(mg_ctx *ctx, const void *f_host, void *psi_host, double *err)
 {
     CTX_OR_FAIL(ctx);
     if (!f_host || !psi_host) return ctx->fail(MG_EINVAL, "mg_step_host: null host pointer");
-    size_t nb = ctx->N * ctx->elem;
-    MG_CK(ctx, cudaMemcpyAsync(ctx->f, f_host, nb, cudaMemcpyHostToDevice, ctx->stream));
-    MG_CK(ctx, cudaMemcpyAsync(ctx->psi, psi_host, nb, cudaMemcpyHostToDevice, ctx->stream));
+    const int top = ctx->nlevels - 1;
+    // bytes the caller's buffers hold: the whole field, or this rank's planes on an NCCL slab
+    size_t nb = (ctx->group && ctx->group->nccl ? ctx->own_elems(top) : ctx->N) * ctx->elem;
+    int rc;
+    if (!ctx->group) {
+        MG_CK(ctx, cudaMemcpyAsync(ctx->f, f_host, nb, cudaMemcpyHostToDevice, ctx->stream));
+        MG_CK(ctx, cudaMemcpyAsync(ctx->psi, psi_host, nb, cudaMemcpyHostToDevice, ctx->stream));
+    } else {
+        if ((rc = ctx->copy_in(MG_BUF_F, ctx->size, f_host, nb))) return rc;
+        if ((rc = ctx->copy_in(MG_BUF_PSI, ctx->size, psi_host, nb))) return rc;
+    }
     double e;
-    int rc = ctx->step(&e);
-    if (rc) return rc;
-    MG_CK(ctx, cudaMemcpyAsync(psi_host, ctx->psi, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    if ((rc = ctx->step(&e))) return rc;
+    if (!ctx->group) MG_CK(ctx, cudaMemcpyAsync(psi_host, ctx->psi, nb, cudaMemcpyDeviceToHost, ctx->stream));
+    else if ((rc = ctx->copy_out(MG_BUF_PSI, ctx->size, psi_host, nb))) return rc;
     if (err) *err = e;
     return ctx->sync();
 }
@@ -435,18 +441,83 @@ int mg_profile_vcycle(mg_ctx *ctx, int cap, int *kind, int *L, int *sweeps, floa
     return MG_OK;
 }
 
-// ------------------------------------------------------------------ multi-GPU slabs
-int mg_create_slab(int dim, int size, int real_kind, int smooth, int device, int rank, int nranks,
-                   mg_ctx **out)
+// ------------------------------------------------------------------ multi-GPU slabs (mg_slab.cuh)
+int mg_nccl_unique_id(void *id, size_t bytes)
 {
-    if (nranks == 1 && rank == 0) return create_common(dim, size, real_kind, smooth, device, 0, 1, out);
-    g_create_error = "mg_create_slab: slab decomposition not implemented yet";
-    if (out) *out = nullptr;
-    return MG_EUNSUPPORTED;
+    if (!id || bytes < sizeof(NcclUniqueId)) return MG_EINVAL;
+    NcclApi *api = NcclApi::get(g_create_error);
+    if (!api) return MG_EUNSUPPORTED;
+    NcclUniqueId u;
+    int e = api->GetUniqueId(&u);
+    if (e) { g_create_error = api->GetErrorString(e); return MG_ECUDA; }
+    memcpy(id, &u, sizeof(u));
+    return MG_OK;
 }
-int mg_slab_ipc_size(void) { return (int)sizeof(cudaIpcMemHandle_t); }
-int mg_slab_export(mg_ctx *ctx, void *, size_t) { return ctx ? ctx->fail(MG_EUNSUPPORTED, "slabs: not implemented") : MG_EINVAL; }
-int mg_slab_attach(mg_ctx *ctx, int, const void *, size_t) { return ctx ? ctx->fail(MG_EUNSUPPORTED, "slabs: not implemented") : MG_EINVAL; }
-int mg_slab_attach_local(mg_ctx *ctx, int, mg_ctx *) { return ctx ? ctx->fail(MG_EUNSUPPORTED, "slabs: not implemented") : MG_EINVAL; }
+
+int mg_create_slab(int dim, int size, int real_kind, int smooth, int device, int rank, int nranks,
+                   const void *nccl_id, size_t id_bytes, mg_ctx **out)
+{
+    if (nranks == 1) return create_common(dim, size, real_kind, smooth, device, 0, 1, out);
+    if (!out || !nccl_id || id_bytes < sizeof(NcclUniqueId) || rank < 0 || rank >= nranks) return MG_EINVAL;
+    NcclApi *api = NcclApi::get(g_create_error);
+    if (!api) return MG_EUNSUPPORTED;
+    int rc = create_common(dim, size, real_kind, smooth, device, rank, nranks, out);
+    if (rc) return rc;
+    mg_ctx *c = *out;
+    SlabGroup *g = new SlabGroup();
+    g->nranks = nranks; g->nccl = true; g->api = api; g->m.push_back(c);
+    NcclUniqueId u;
+    memcpy(&u, nccl_id, sizeof(u));
+    int e = api->CommInitRank(&g->comm, nranks, u, rank);
+    if (e) {
+        g_create_error = std::string("ncclCommInitRank: ") + api->GetErrorString(e);
+        delete g; c->release(); delete c; *out = nullptr;
+        return MG_ECUDA;
+    }
+    c->group = g; c->owns_group = true;
+    return MG_OK;
+}
+
+// every slab in this process, on one device and one stream: the slab schedule on a single GPU
+int mg_create_slab_local(int dim, int size, int real_kind, int smooth, int device, int nslabs, mg_ctx **out)
+{
+    if (nslabs == 1) return create_common(dim, size, real_kind, smooth, device, 0, 1, out);
+    if (!out) return MG_EINVAL;
+    SlabGroup *g = new SlabGroup();
+    g->nranks = nslabs;
+    for (int r = 0; r < nslabs; ++r) {
+        mg_ctx *c = nullptr;
+        int rc = create_common(dim, size, real_kind, smooth, device, r, nslabs, &c);
+        if (rc) {
+            for (mg_ctx *m : g->m) { m->release(); delete m; }
+            delete g; *out = nullptr;
+            return rc;
+        }
+        if (r > 0) {  // one stream for the whole group
+            cudaStreamDestroy(c->own_stream);
+            c->own_stream = g->m[0]->own_stream;
+            c->stream = g->m[0]->stream;
+        }
+        c->group = g;
+        g->m.push_back(c);
+    }
+    g->m[0]->owns_group = true;
+    *out = g->m[0];
+    return MG_OK;
+}
+
+int mg_slab_info(mg_ctx *ctx, int *rank, int *nranks, int *own_planes, int *ghost, uint64_t *exchanges,
+                 uint64_t *exchanged_bytes)
+{
+    if (!ctx) return MG_EINVAL;
+    const int top = ctx->nlevels - 1;
+    if (rank) *rank = ctx->rank;
+    if (nranks) *nranks = ctx->nranks;
+    if (own_planes) *own_planes = ctx->dist[top] ? ctx->nzl[top] : ctx->size;
+    if (ghost) *ghost = ctx->G;
+    if (exchanges) *exchanges = ctx->group ? ctx->group->exchanges : 0;
+    if (exchanged_bytes) *exchanged_bytes = ctx->group ? ctx->group->exchanged_bytes : 0;
+    return MG_OK;
+}
 
 }  // extern "C"

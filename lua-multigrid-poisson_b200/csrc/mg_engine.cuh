@@ -15,6 +15,7 @@
 #include "mg_fused_simple.cuh"
 #include "mg_math.cuh"
 #include "mg_ops_ref.cuh"
+#include "mg_slab.cuh"
 #include "mg_small.cuh"
 #include "mg_stream3d.cuh"
 #include "mg_warp2d.cuh"
@@ -62,8 +63,10 @@ struct mg_ctx {
     int stream_flags = 0;    // debug switches of the streaming smoother (see Stream3DArgs::flags)
     int tz_override = 0;     // planes per CTA of the streaming smoother (0 = cost model)
     // TMA descriptors of the source fields, keyed by (pointer, level width, box x, box y)
-    std::map<std::tuple<const void *, int, int, int>, CUtensorMap> tmaps;
-    int tensor_map(const void *base, int L, int box_x, int box_y, const CUtensorMap **out);
+    std::map<std::tuple<const void *, int, int, int, int>, CUtensorMap> tmaps;
+    int tensor_map(const void *base, int L, int nplanes, int box_x, int box_y, const CUtensorMap **out);
+    int copy_in(int which, int lv, const void *host, size_t bytes);
+    int copy_out(int which, int lv, void *host, size_t bytes);
 
     // ---- grid-hierarchy arena (K-f): one allocation, zero-filled once (cpu-raw.lua:159-171)
     void *arena = nullptr;
@@ -96,12 +99,21 @@ struct mg_ctx {
     std::vector<mg::TraceRec> trace;
     mg::Engine *eng = nullptr;
 
-    size_t level_elems(int lv) const
-    {
-        size_t L = (size_t)1 << lv;
-        return L * L * (dim == 3 ? L : 1);
-    }
+    // ---- slab decomposition (mg_slab.cuh); single GPU: G = 0, nothing distributed
+    int G = 0;                          // ghost planes on each side of a distributed level
+    bool dist[mg::MAX_LEVELS] = {};     // level is cut across the ranks
+    int nzl[mg::MAX_LEVELS] = {};       // planes owned by each rank at a distributed level
+    mg::SlabGroup *group = nullptr;
+    bool owns_group = false, f_ghost_dirty = true;
+    size_t Ntop = 0;                    // elements allocated for a top-level field (incl. ghosts)
+
+    int planes(int lv) const { return dist[lv] ? nzl[lv] + 2 * G : (dim == 3 ? (1 << lv) : 1); }
+    size_t plane_elems(int lv) const { size_t L = (size_t)1 << lv; return L * L; }
+    size_t level_elems(int lv) const { return plane_elems(lv) * (size_t)planes(lv); }
     size_t level_bytes(int lv) const { return level_elems(lv) * elem; }
+    size_t own_off_elems(int lv) const { return dist[lv] ? (size_t)G * plane_elems(lv) : 0; }
+    size_t own_elems(int lv) const { return dist[lv] ? (size_t)nzl[lv] * plane_elems(lv) : level_elems(lv); }
+    size_t arena_off(const void *p) const { return (size_t)((const char *)p - (const char *)arena); }
 
     int fail(int code, const char *msg)
     {
@@ -171,6 +183,8 @@ struct Engine {
     virtual int twogrid_fused(mg_ctx *c, double h, void *u, const void *f, int lv) = 0;
     virtual int frob_err(mg_ctx *c, double *err, bool materialise) = 0;
     virtual int residual_norm(mg_ctx *c, double *rms) = 0;
+    virtual int slab_vcycle(SlabGroup *g) = 0;
+    virtual int frob_partial_sum(mg_ctx *c, double *sum) = 0;
 };
 
 static inline dim3 grid_for(int dim, int L, dim3 b)
@@ -195,9 +209,17 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
     // ------------------------------------------------------------ reference operators
     int init_cells(mg_ctx *c) override
     {
+        const int top = c->nlevels - 1;
         dim3 b = block_for(c->size), g = grid_for(DIM, c->size, b);
-        k_init_cells<R, A, DIM><<<g, b, 0, c->stream>>>((R *)c->f, (R *)c->psi, c->size);
+        int plane0 = 0, k0 = 0;
+        if (c->dist[top]) {  // owned planes only: ghosts outside the grid must stay +0
+            g.z = (unsigned)c->nzl[top];
+            plane0 = c->G;
+            k0 = c->rank * c->nzl[top];
+        }
+        k_init_cells<R, A, DIM><<<g, b, 0, c->stream>>>((R *)c->f, (R *)c->psi, c->size, plane0, k0);
         MG_LAUNCH_CHECK(c);
+        c->f_ghost_dirty = true;
         return MG_OK;
     }
     int jacobi(mg_ctx *c, int L, void *dest, const void *u, const void *f, double h) override
@@ -296,15 +318,26 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
     // cur + prolong(Vp), followed optionally by Rout = restrict(f - A cur).
     // ---- streaming (TMA, temporally blocked) smoother passes, 3-D only
     template <int S, bool PRO, bool RES>
-    int launch_stream3d(mg_ctx *c, int L, R *dst, const R *src, const R *f, const R *Vp, R *Rout, const Coef<A> &cf)
+    int launch_stream3d(mg_ctx *c, int lv, R *dst, const R *src, const R *f, const R *Vp, R *Rout, const Coef<A> &cf)
     {
+        const int L = 1 << lv;
         // in-plane tile: 64 x 32 for 4-byte reals, 32 x 32 for 8-byte reals (shared-memory budget)
         constexpr int TX = sizeof(R) == 4 ? 64 : 32, TY = 32;
         typedef Stream3DCfg<R, S, RES, TX, TY> C;
         const CUtensorMap *map = nullptr, *fmap = nullptr;
-        int rc = c->tensor_map(src, L, C::WX, C::WY, &map);
+        const int nplanes = c->planes(lv);
+        int rc = c->tensor_map(src, L, nplanes, C::WX, C::WY, &map);
         if (rc) return rc;
-        if ((rc = c->tensor_map(f, L, C::WX, C::WY, &fmap))) return rc;
+        if ((rc = c->tensor_map(f, L, nplanes, C::WX, C::WY, &fmap))) return rc;
+        // slab view of this level (single GPU / replicated level: the whole cube)
+        int nz_lo = 0, nz_hi = L, zdom0 = 0, rz_off = 0, vz_off = 0;
+        if (c->dist[lv]) {
+            const int zg0 = c->rank * c->nzl[lv];        // global index of the first owned plane
+            nz_lo = c->G; nz_hi = c->G + c->nzl[lv]; zdom0 = c->G - zg0;
+            rz_off = c->dist[lv - 1] ? c->G : zg0 / 2;   // coarse slab array, or replicated cube
+            vz_off = c->dist[lv - 1] ? c->G - zg0 / 2 : 0;
+        }
+        const int nown = nz_hi - nz_lo;
         auto kern = k_stream3d<R, A, S, PRO, RES, TX, TY>;
         MG_CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         // planes per CTA: minimise waves x steps-per-CTA on 148 SMs (one CTA per SM)
@@ -312,26 +345,26 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         if (TZ <= 0) {
             const long tiles = (long)((L + TX - 1) / TX) * ((L + TY - 1) / TY);
             long best = -1;
-            for (int cand = L; cand >= 8; cand >>= 1) {
-                long ncta = tiles * (L / cand);
+            for (int cand = nown; cand >= 8; cand >>= 1) {
+                long ncta = tiles * ((nown + cand - 1) / cand);
                 long cost = ((ncta + 147) / 148) * (cand + 3 * C::H);
                 if (best < 0 || cost < best) { best = cost; TZ = cand; }
             }
         }
-        if (TZ > L) TZ = L;
+        if (TZ > nown) TZ = nown;
         TZ &= ~1;
-        dim3 grid((L + TX - 1) / TX, (L + TY - 1) / TY, (L + TZ - 1) / TZ);
-        Stream3DArgs<R> a{dst, Vp, Rout, L, TZ, c->stream_flags, 0, L, 0, L, 0, 0};
+        dim3 grid((L + TX - 1) / TX, (L + TY - 1) / TY, (nown + TZ - 1) / TZ);
+        Stream3DArgs<R> a{dst, Vp, Rout, L, TZ, c->stream_flags, nz_lo, nz_hi, zdom0, zdom0 + L, rz_off, vz_off};
         c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : (RES ? MG_K_SWEEP_RESTRICT : MG_K_SWEEP), L, S);
         kern<<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(*map, *fmap, a, cf);
         c->prof_end();
         MG_LAUNCH_CHECK(c);
         return MG_OK;
     }
-    int stream3d_pass(mg_ctx *c, int L, int S, bool pro, bool res, R *dst, const R *src, const R *f,
+    int stream3d_pass(mg_ctx *c, int lv, int S, bool pro, bool res, R *dst, const R *src, const R *f,
                       const R *Vp, R *Rout, const Coef<A> &cf)
     {
-#define MG_S3D(S_, P_, R_) return launch_stream3d<S_, P_, R_>(c, L, dst, src, f, Vp, Rout, cf)
+#define MG_S3D(S_, P_, R_) return launch_stream3d<S_, P_, R_>(c, lv, dst, src, f, Vp, Rout, cf)
         if (!pro && !res) {
             switch (S) { case 1: MG_S3D(1, false, false); case 2: MG_S3D(2, false, false);
                          case 3: MG_S3D(3, false, false); case 4: MG_S3D(4, false, false); }
@@ -345,23 +378,148 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
 #undef MG_S3D
         return c->fail(MG_EINVAL, "stream3d_pass: unsupported combination");
     }
-    int sweeps_stream3d(mg_ctx *c, int L, R *&cur, R *&oth, const R *f, const Coef<A> &cf, int n,
-                        const R *Vp, R *Rout)
+    // split n sweeps into passes of <= tb sweeps; with a fused residual stage the last pass has <= 3
+    static int plan_passes(int n, int tb, bool has_res, int *plan)
     {
-        const int tb = c->tb;
-        int plan[64], np = 0, rem = n, last = 0;
-        if (Rout) { last = n < 3 ? n : 3; if (last > tb) last = tb; rem = n - last; }
+        int np = 0, rem = n, last = 0;
+        if (has_res) { last = n < 3 ? n : 3; if (last > tb) last = tb; rem = n - last; }
         if (rem > 0) {
             int k = (rem + tb - 1) / tb, base = rem / k, extra = rem % k;
             for (int i = 0; i < k; ++i) plan[np++] = base + (i < extra ? 1 : 0);
         }
-        if (Rout) plan[np++] = last;
+        if (has_res) plan[np++] = last;
+        return np;
+    }
+    int sweeps_stream3d(mg_ctx *c, int lv, R *&cur, R *&oth, const R *f, const Coef<A> &cf, int n,
+                        const R *Vp, R *Rout)
+    {
+        int plan[64];
+        const int np = plan_passes(n, c->tb, Rout != nullptr, plan);
         for (int i = 0; i < np; ++i) {
-            int rc = stream3d_pass(c, L, plan[i], i == 0 && Vp, i == np - 1 && Rout, oth, cur, f, Vp, Rout, cf);
+            int rc = stream3d_pass(c, lv, plan[i], i == 0 && Vp, i == np - 1 && Rout, oth, cur, f, Vp, Rout, cf);
             if (rc) return rc;
             R *t = cur; cur = oth; oth = t;
         }
         return MG_OK;
+    }
+
+    // ---- slab V-cycle (mg_slab.cuh): the same schedule on every rank, halo planes in between
+    static char *at(mg_ctx *c, size_t off) { return (char *)c->arena + off; }
+    int slab_exchange(SlabGroup *g, size_t off, int lv, int depth)
+    {
+        mg_ctx *c0 = g->m[0];
+        const size_t pb = c0->plane_elems(lv) * c0->elem;
+        const int G = c0->G, nz = c0->nzl[lv];
+        const size_t nb = (size_t)depth * pb;
+        if (g->nccl) {
+            mg_ctx *c = c0;
+            char *b = at(c, off);
+            NcclApi *api = g->api;
+            int e = api->GroupStart();
+            if (c->rank > 0) {
+                if (!e) e = api->Send(b + (size_t)G * pb, nb, NcclApi::kInt8, c->rank - 1, g->comm, c->stream);
+                if (!e) e = api->Recv(b + (size_t)(G - depth) * pb, nb, NcclApi::kInt8, c->rank - 1, g->comm, c->stream);
+            }
+            if (c->rank < g->nranks - 1) {
+                if (!e) e = api->Send(b + (size_t)(G + nz - depth) * pb, nb, NcclApi::kInt8, c->rank + 1, g->comm, c->stream);
+                if (!e) e = api->Recv(b + (size_t)(G + nz) * pb, nb, NcclApi::kInt8, c->rank + 1, g->comm, c->stream);
+            }
+            int e2 = api->GroupEnd();
+            if (e || e2) return c->fail(MG_ECUDA, api->GetErrorString(e ? e : e2));
+        } else {
+            for (int r = 0; r < g->nranks; ++r) {
+                mg_ctx *c = g->m[r];
+                if (r > 0)
+                    MG_CK(c, cudaMemcpyAsync(at(c, off) + (size_t)(G - depth) * pb,
+                                             at(g->m[r - 1], off) + (size_t)(G + nz - depth) * pb, nb,
+                                             cudaMemcpyDeviceToDevice, c0->stream));
+                if (r < g->nranks - 1)
+                    MG_CK(c, cudaMemcpyAsync(at(c, off) + (size_t)(G + nz) * pb, at(g->m[r + 1], off) + (size_t)G * pb,
+                                             nb, cudaMemcpyDeviceToDevice, c0->stream));
+            }
+        }
+        g->exchanges++;
+        g->exchanged_bytes += 2 * nb;
+        return MG_OK;
+    }
+    // replicated level lv: every rank has produced planes [r*L/P, (r+1)*L/P) of the cube
+    int slab_allgather(SlabGroup *g, size_t off, int lv)
+    {
+        mg_ctx *c0 = g->m[0];
+        const size_t part = c0->plane_elems(lv) * c0->elem * (size_t)((1 << lv) / g->nranks);
+        if (g->nccl) {
+            char *b = at(c0, off);
+            int e = g->api->AllGather(b + (size_t)c0->rank * part, b, part, NcclApi::kInt8, g->comm, c0->stream);
+            if (e) return c0->fail(MG_ECUDA, g->api->GetErrorString(e));
+        } else {
+            for (int r = 0; r < g->nranks; ++r)
+                for (int o = 0; o < g->nranks; ++o)
+                    if (o != r)
+                        MG_CK(c0, cudaMemcpyAsync(at(g->m[r], off) + (size_t)o * part, at(g->m[o], off) + (size_t)o * part,
+                                                  part, cudaMemcpyDeviceToDevice, c0->stream));
+        }
+        return MG_OK;
+    }
+    int slab_twogrid(SlabGroup *g, double h, size_t u_off, size_t f_off, int lv)
+    {
+        mg_ctx *c0 = g->m[0];
+        int rc;
+        if (!c0->dist[lv]) {  // replicated: every rank runs the ordinary single-GPU path
+            for (mg_ctx *c : g->m)
+                if ((rc = twogrid_fused(c, h, at(c, u_off), at(c, f_off), lv))) return rc;
+            return MG_OK;
+        }
+        if constexpr (DIM == 3) {
+            const Coef<A> cf = make_coef<A>(DIM, h);
+            const size_t W_off = c0->arena_off(c0->W[lv]);
+            const size_t Rc_off = c0->arena_off(c0->R[lv - 1]), Vc_off = c0->arena_off(c0->V[lv - 1]);
+            size_t cur = u_off, oth = W_off;
+            int plan[64];
+            // pre-smoothing, residual + restriction fused into the last pass (cpu-raw.lua:198-218)
+            int np = plan_passes(c0->smooth, c0->tb, true, plan);
+            for (int i = 0; i < np; ++i) {
+                const bool res = i == np - 1;
+                if ((rc = slab_exchange(g, cur, lv, plan[i] + (res ? 1 : 0)))) return rc;
+                for (mg_ctx *c : g->m)
+                    if ((rc = stream3d_pass(c, lv, plan[i], false, res, (R *)at(c, oth), (const R *)at(c, cur),
+                                            (const R *)at(c, f_off), nullptr, res ? (R *)at(c, Rc_off) : nullptr, cf)))
+                        return rc;
+                size_t t = cur; cur = oth; oth = t;
+            }
+            // the restricted residual is the next level's right-hand side
+            if (c0->dist[lv - 1]) rc = slab_exchange(g, Rc_off, lv - 1, c0->G);
+            else rc = slab_allgather(g, Rc_off, lv - 1);
+            if (rc) return rc;
+            if ((rc = slab_twogrid(g, 2 * h, Vc_off, Rc_off, lv - 1))) return rc;   // cpu-raw.lua:221-222
+            if (c0->dist[lv - 1] && (rc = slab_exchange(g, Vc_off, lv - 1, 2))) return rc;
+            // prolongation + add fused into the first post-smoothing pass (cpu-raw.lua:225-236)
+            np = plan_passes(c0->smooth, c0->tb, false, plan);
+            for (int i = 0; i < np; ++i) {
+                if ((rc = slab_exchange(g, cur, lv, plan[i]))) return rc;
+                for (mg_ctx *c : g->m)
+                    if ((rc = stream3d_pass(c, lv, plan[i], i == 0, false, (R *)at(c, oth), (const R *)at(c, cur),
+                                            (const R *)at(c, f_off), i == 0 ? (const R *)at(c, Vc_off) : nullptr, nullptr, cf)))
+                        return rc;
+                size_t t = cur; cur = oth; oth = t;
+            }
+            if (cur != u_off)
+                for (mg_ctx *c : g->m)
+                    MG_CK(c, cudaMemcpyAsync(at(c, u_off), at(c, cur), c->level_bytes(lv), cudaMemcpyDeviceToDevice, c0->stream));
+            return MG_OK;
+        } else {
+            return c0->fail(MG_EUNSUPPORTED, "slab decomposition is 3-D only");
+        }
+    }
+    int slab_vcycle(SlabGroup *g) override
+    {
+        mg_ctx *c0 = g->m[0];
+        const int top = c0->nlevels - 1;
+        if (c0->f_ghost_dirty) {  // f is static between uploads: its ghosts are exchanged once
+            int rc = slab_exchange(g, c0->arena_off(c0->f), top, c0->G);
+            if (rc) return rc;
+            for (mg_ctx *c : g->m) c->f_ghost_dirty = false;
+        }
+        return slab_twogrid(g, 1.0 / c0->size, c0->arena_off(c0->psi), c0->arena_off(c0->f), top);
     }
 
     // ---- 2-D warp-streaming smoother passes
@@ -424,7 +582,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         }
         if constexpr (DIM == 3) {
             if (c->tb >= 1 && L >= c->stream_min_L && n >= 1 && !(Vp && Rout && n <= c->tb))
-                return sweeps_stream3d(c, L, cur, oth, f, cf, n, Vp, Rout);
+                return sweeps_stream3d(c, lv, cur, oth, f, cf, n, Vp, Rout);
         }
         dim3 b = block_for(L), g = grid_for(DIM, L, b);
         for (int s = 0; s < n; ++s) {
@@ -544,6 +702,28 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             int rc = c->ensure_debug_arena();
             if (rc) return rc;
         }
+        if (c->group) {  // slabs: every rank sums its owned planes, then the sums are added
+            SlabGroup *g = c->group;
+            double tot = 0;
+            if (g->nccl) {
+                int rc = frob_partial_sum(c, nullptr);
+                if (rc) return rc;
+                int e = g->api->AllReduce(c->d_scalar, c->d_scalar, 1, NcclApi::kFloat64, NcclApi::kSum, g->comm, c->stream);
+                if (e) return c->fail(MG_ECUDA, g->api->GetErrorString(e));
+                MG_CK(c, cudaMemcpyAsync(c->h_scalar, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+                MG_CK(c, cudaStreamSynchronize(c->stream));
+                tot = *c->h_scalar;
+            } else {
+                for (mg_ctx *m : g->m) {
+                    double part;
+                    int rc = frob_partial_sum(m, &part);
+                    if (rc) return rc;
+                    tot += part;
+                }
+            }
+            *err = std::sqrt(tot / (double)c->N);
+            return MG_OK;
+        }
         k_frob_partial<R, A><<<c->npartial, 256, 0, c->stream>>>(
             (const R *)c->psi, (const R *)c->psiOld, materialise ? (R *)c->errorBuf : nullptr, c->N,
             c->d_partial);
@@ -554,8 +734,22 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         *err = std::sqrt(s / (double)c->N);
         return MG_OK;
     }
+    // sum of (psi - psiOld)^2 over the planes this rank owns; sum == nullptr leaves it in d_scalar
+    int frob_partial_sum(mg_ctx *c, double *sum) override
+    {
+        const int top = c->nlevels - 1;
+        const size_t o = c->own_off_elems(top), n = c->own_elems(top);
+        k_frob_partial<R, A><<<c->npartial, 256, 0, c->stream>>>((const R *)c->psi + o, (const R *)c->psiOld + o,
+                                                                 nullptr, n, c->d_partial);
+        MG_LAUNCH_CHECK(c);
+        if (sum) return reduce_to_host(c, sum);
+        k_final_sum<<<1, 1024, 0, c->stream>>>(c->d_partial, c->npartial, c->d_scalar);
+        MG_LAUNCH_CHECK(c);
+        return MG_OK;
+    }
     int residual_norm(mg_ctx *c, double *rms) override
     {
+        if (c->group) return c->fail(MG_EUNSUPPORTED, "mg_residual_norm: not available on slabs yet");
         // uses the partner of psi as scratch for r; W[top] is free outside a V-cycle
         const int top = c->nlevels - 1;
         R *scratch = (R *)c->W[top];
@@ -582,7 +776,21 @@ inline int mg_ctx::init(int dim_, int size_, int real_kind_, int smooth_, int de
     while ((1 << nlevels) < size) ++nlevels;
     ++nlevels;
     if (nlevels > mg::MAX_LEVELS) return fail(MG_EINVAL, "too many levels");
-    N = level_elems(nlevels - 1);
+    if (nranks > 1) {  // slab decomposition along z (mg_slab.cuh)
+        if (dim != 3) return fail(MG_EUNSUPPORTED, "slab decomposition is 3-D only");
+        if (nranks > 8 || (nranks & (nranks - 1))) return fail(MG_EINVAL, "nranks must be 2, 4 or 8");
+        G = 4;
+        for (int lv = 0; lv < nlevels; ++lv) {
+            const int L = 1 << lv;
+            if (L >= 64 && L / nranks >= 8) { dist[lv] = true; nzl[lv] = L / nranks; }
+        }
+        if (!dist[nlevels - 1]) return fail(MG_EINVAL, "grid too small to be cut into slabs (need size >= 64 and size/nranks >= 8)");
+        stream_min_L = 64;
+        tb = 4;
+        use_graph = 0;
+    }
+    N = (size_t)size * size * (dim == 3 ? (size_t)size : 1);
+    Ntop = level_elems(nlevels - 1);
     small_L = dim == 3 ? 16 : 64;
     tb2 = real_kind == MG_REAL_F32 ? 7 : 4;  // double arithmetic: 8 pipeline stages would spill
     int ndev = 0;
@@ -600,9 +808,9 @@ inline int mg_ctx::init(int dim_, int size_, int real_kind_, int smooth_, int de
     auto up = [](size_t x) { return (x + mg::ARENA_ALIGN - 1) / mg::ARENA_ALIGN * mg::ARENA_ALIGN; };
     const int top = nlevels - 1;
     size_t off = 0;
-    size_t o_f = off; off += up(N * elem);
-    size_t o_psi = off; off += up(N * elem);
-    size_t o_old = off; off += up(N * elem);
+    size_t o_f = off; off += up(Ntop * elem);
+    size_t o_psi = off; off += up(Ntop * elem);
+    size_t o_old = off; off += up(Ntop * elem);
     size_t o_R[mg::MAX_LEVELS], o_V[mg::MAX_LEVELS], o_W[mg::MAX_LEVELS];
     for (int lv = 0; lv <= top; ++lv) {
         if (lv < top) {
@@ -647,6 +855,19 @@ inline int mg_ctx::init(int dim_, int size_, int real_kind_, int smooth_, int de
 inline void mg_ctx::release()
 {
     if (device >= 0) cudaSetDevice(device);
+    if (group && owns_group) {
+        mg::SlabGroup *g = group;
+        if (own_stream) cudaStreamSynchronize(stream);
+        for (size_t r = 1; r < g->m.size(); ++r) {  // LOCAL: the other slabs belong to rank 0's handle
+            g->m[r]->group = nullptr;
+            g->m[r]->own_stream = nullptr;         // shared with rank 0
+            g->m[r]->release();
+            delete g->m[r];
+        }
+        if (g->nccl && g->comm) g->api->CommDestroy(g->comm);
+        delete g;
+        group = nullptr;
+    }
     drop_graph();
     if (own_stream) cudaStreamSynchronize(own_stream);
     if (arena) cudaFree(arena);
@@ -666,6 +887,7 @@ inline int mg_ctx::ensure_debug_arena()
     auto up = [](size_t x) { return (x + mg::ARENA_ALIGN - 1) / mg::ARENA_ALIGN * mg::ARENA_ALIGN; };
     const int top = nlevels - 1;
     size_t off = 0;
+    if (nranks > 1) return fail(MG_EUNSUPPORTED, "the reference-sequence mode is single-GPU only");
     size_t o_err = off; off += up(N * elem);
     size_t o_tmp = off; off += up(N * elem);
     size_t o_Rt = off; off += up(N * elem);
@@ -715,9 +937,9 @@ inline void *mg_ctx::buffer(int which, int level, size_t *cap)
 
 // TMA descriptor of a dense L^3 field with a (box_x, box_y, 1) box; out-of-bounds elements are
 // zero-filled, which is the reference's Dirichlet rule (cpu-raw.lua:36-39).
-inline int mg_ctx::tensor_map(const void *base, int L, int box_x, int box_y, const CUtensorMap **out)
+inline int mg_ctx::tensor_map(const void *base, int L, int nplanes, int box_x, int box_y, const CUtensorMap **out)
 {
-    auto key = std::make_tuple(base, L, box_x, box_y);
+    auto key = std::make_tuple(base, L, nplanes, box_x, box_y);
     auto it = tmaps.find(key);
     if (it != tmaps.end()) { *out = &it->second; return MG_OK; }
     typedef CUresult (*EncodeFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
@@ -733,7 +955,7 @@ inline int mg_ctx::tensor_map(const void *base, int L, int box_x, int box_y, con
         encode = (EncodeFn)fn;
     }
     CUtensorMap m;
-    cuuint64_t gdim[3] = {(cuuint64_t)L, (cuuint64_t)L, (cuuint64_t)L};
+    cuuint64_t gdim[3] = {(cuuint64_t)L, (cuuint64_t)L, (cuuint64_t)nplanes};
     cuuint64_t gstr[2] = {(cuuint64_t)L * elem, (cuuint64_t)L * L * elem};
     cuuint32_t box[3] = {(cuuint32_t)box_x, (cuuint32_t)box_y, 1};
     cuuint32_t est[3] = {1, 1, 1};
@@ -748,6 +970,56 @@ inline int mg_ctx::tensor_map(const void *base, int L, int box_x, int box_y, con
     auto ins = tmaps.emplace(key, m);
     *out = &ins.first->second;
     return MG_OK;
+}
+
+// Host <-> device for one buffer. Single GPU: the whole field. NCCL slab: the planes this rank
+// owns (nzl * L^2 elements). LOCAL slab group: the GLOBAL field, scattered / gathered over the
+// member slabs (replicated levels are written to every member and read from rank 0).
+static inline int mg_copy_impl(mg_ctx *c, int which, int level, void *host, size_t bytes, bool in)
+{
+    size_t cap = 0;
+    void *d0 = c->buffer(which, level, &cap);
+    if (!d0 || !host) return c->fail(MG_EINVAL, "no such buffer (or not materialised in this mode)");
+    int lv = c->nlevels - 1;
+    if (which >= MG_BUF_r) { lv = 0; while ((1 << lv) < level) ++lv; }
+    auto cp = [&](void *dev, void *h, size_t nb) -> cudaError_t {
+        return in ? cudaMemcpyAsync(dev, h, nb, cudaMemcpyHostToDevice, c->stream)
+                  : cudaMemcpyAsync(h, dev, nb, cudaMemcpyDeviceToHost, c->stream);
+    };
+    if (!c->group) {
+        if (bytes > cap) return c->fail(MG_EINVAL, "too many bytes for this buffer");
+        MG_CK(c, cp(d0, host, bytes));
+    } else if (c->group->nccl) {
+        const size_t own = c->own_elems(lv) * c->elem;
+        if (bytes > own) return c->fail(MG_EINVAL, "too many bytes for this rank's slab");
+        MG_CK(c, cp((char *)d0 + c->own_off_elems(lv) * c->elem, host, bytes));
+    } else {
+        const size_t full = c->plane_elems(lv) * c->elem * ((size_t)1 << lv);
+        if (bytes != full) return c->fail(MG_EINVAL, "slab group: pass the whole global field");
+        const size_t off = c->arena_off(d0);
+        for (size_t r = 0; r < c->group->m.size(); ++r) {
+            mg_ctx *m = c->group->m[r];
+            char *dev = (char *)m->arena + off;
+            if (c->dist[lv]) {
+                const size_t own = c->own_elems(lv) * c->elem;
+                MG_CK(c, cp(dev + c->own_off_elems(lv) * c->elem, (char *)host + r * own, own));
+            } else if (in || r == 0) {
+                MG_CK(c, cp(dev, host, full));
+            }
+        }
+    }
+    if (in && which == MG_BUF_F)
+        for (mg_ctx *m : (c->group ? c->group->m : std::vector<mg_ctx *>{c})) m->f_ghost_dirty = true;
+    MG_CK(c, cudaStreamSynchronize(c->stream));
+    return MG_OK;
+}
+inline int mg_ctx::copy_in(int which, int lv, const void *host, size_t bytes)
+{
+    return mg_copy_impl(this, which, lv, const_cast<void *>(host), bytes, true);
+}
+inline int mg_ctx::copy_out(int which, int lv, void *host, size_t bytes)
+{
+    return mg_copy_impl(this, which, lv, host, bytes, false);
 }
 
 inline void mg_ctx::drop_graph()
@@ -767,6 +1039,7 @@ inline int mg_ctx::vcycle()
         if (rc) return rc;
         return eng->twogrid_refseq(this, h, psi, f, top);
     }
+    if (group) return eng->slab_vcycle(group);
     if (!use_graph) return eng->twogrid_fused(this, h, psi, f, top);
     if (!gexec) {
         cudaStream_t saved = stream;
@@ -791,7 +1064,12 @@ inline int mg_ctx::vcycle()
 // loop body of run() (cpu-raw.lua:246-254)
 inline int mg_ctx::step(double *err_out)
 {
-    MG_CK(this, cudaMemcpyAsync(psiOld, psi, N * elem, cudaMemcpyDeviceToDevice, stream));
+    if (group) {
+        for (mg_ctx *m : group->m)
+            MG_CK(this, cudaMemcpyAsync(m->psiOld, m->psi, Ntop * elem, cudaMemcpyDeviceToDevice, stream));
+    } else {
+        MG_CK(this, cudaMemcpyAsync(psiOld, psi, Ntop * elem, cudaMemcpyDeviceToDevice, stream));
+    }
     int rc = vcycle();
     if (rc) return rc;
     double e;

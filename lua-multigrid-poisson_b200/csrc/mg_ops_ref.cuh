@@ -9,13 +9,15 @@ namespace mg {
 
 // cpu-raw.lua:8-20 initCells / gpu.lua:41-59 init
 template <typename R, typename A, int DIM>
-__global__ void k_init_cells(R *__restrict__ f, R *__restrict__ psi, int L)
+__global__ void k_init_cells(R *__restrict__ f, R *__restrict__ psi, int L, int plane0, int kglobal0)
 {
+    // slab view: local plane plane0 + blockIdx.z holds global plane kglobal0 + blockIdx.z
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = blockIdx.y * blockDim.y + threadIdx.y;
-    int k = DIM == 3 ? blockIdx.z : 0;
+    int kl = DIM == 3 ? plane0 + (int)blockIdx.z : 0;
+    int k = DIM == 3 ? kglobal0 + (int)blockIdx.z : 0;
     if (i >= L || j >= L) return;
-    size_t idx = (size_t)i + (size_t)L * ((size_t)j + (size_t)L * k);
+    size_t idx = (size_t)i + (size_t)L * ((size_t)j + (size_t)L * kl);
     int center = L / 2;
     A value = (A)0;
     if (i == center && j == center && (DIM == 2 || k == center)) value = -(A)1e+6 / (A)1;

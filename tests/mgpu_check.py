@@ -1,0 +1,53 @@
+"""Multi-GPU parity check, run under torchrun with one process per GPU:
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+        --master-port 29511 tests/mgpu_check.py [size]
+
+Every rank runs its slab through NCCL halo exchange; rank 0 gathers the slabs and compares
+them, bit for bit, with a single-GPU solver of the whole grid (which the -m gpu tests tie to
+the oracle). Prints one line per check and exits non-zero on any mismatch."""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from __graft_entry__ import load_package  # noqa: E402
+
+
+def main():
+    size = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    pkg = load_package()
+    ok = True
+    for real in ("float", "double"):
+        s = pkg.create_distributed(size, real, dim=3)
+        errs = [s.step() for _ in range(3)]
+        mine = torch.from_numpy(s.psi.download()).cuda()
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        if rank == 0:
+            full = torch.cat(parts, 0).cpu().numpy()
+            one = pkg.MultigridCUDA(size, real, dim=3, out=False, device=local)
+            one.set_tuning(tb=4)
+            one.set_option("stream_min_L", 64)
+            ref_errs = [one.step() for _ in range(3)]
+            same = full.tobytes() == one.psi.download().tobytes()
+            eok = all(abs(a - b) <= 1e-9 * abs(b) for a, b in zip(errs, ref_errs))
+            print(f"[mgpu_check] {world} GPUs, {size}^3 {real}: psi bit-identical to 1 GPU: {same}; "
+                  f"err {errs} vs {ref_errs}: {eok}; slab info {s.slab_info()}", flush=True)
+            ok = ok and same and eok
+            one.close()
+        s.close()
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    dist.destroy_process_group()
+    sys.exit(0 if int(flag.item()) else 1)
+
+
+if __name__ == "__main__":
+    main()
