@@ -225,8 +225,20 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     elem = 8 if args.real == "double" else 4
-    s = pkg.MultigridCUDA(args.size, args.real, dim=args.dim, device=local, out=False)
-    s.set_tuning(tb=args.tb, small_L=args.small_L, use_graph=0 if args.no_graph else 1)
+    # N > 1: BASELINE config [3], the 3-D 1024^3 grid cut into z-slabs with NCCL halo exchange.
+    # One "unit" of work is a V-cycle of the N=1 workload (512^3 points); `value` is the
+    # whole-job rate in those units, i.e. (global points / 512^3) x V-cycles/s.
+    gsize = args.size
+    if world > 1:
+        gsize = args.mgpu_size
+        s = pkg.create_distributed(gsize, args.real, dim=args.dim)
+    else:
+        s = pkg.MultigridCUDA(args.size, args.real, dim=args.dim, device=local, out=False)
+    unit_scale = (float(gsize) / args.size) ** args.dim if world > 1 else 1.0
+    if world == 1:
+        s.set_tuning(tb=args.tb, small_L=args.small_L, use_graph=0 if args.no_graph else 1)
+    elif args.tb >= 0:
+        s.set_tuning(tb=args.tb)
     for kv in args.opt:
         k, v = kv.split("=")
         s.set_option(k, int(v))
@@ -262,8 +274,8 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
     ms_per_step = ms / args.steps
-    value = world * 1e3 / ms_per_step  # replicas: every rank runs the same workload
-    finite = bool(np.isfinite(s.residual_norm()))
+    value = unit_scale * 1e3 / ms_per_step
+    finite = bool(np.isfinite(s.step()))
 
     # ---- per-launch CUDA-event timing of the same V-cycle (ungraphed), median of 5 cycles
     peak, peak_src = measured_peak()
@@ -281,7 +293,7 @@ def run_ours(args):
     total_prof = sum(g["ms"] for g in groups.values())
     (dk, dL, dsw), dg = max(groups.items(), key=lambda kv: kv[1]["ms"])
     dom_ms = dg["ms"] / dg["n"]
-    dom_bytes = launch_bytes(dk, args.dim, dL, dsw, elem)
+    dom_bytes = launch_bytes(dk, args.dim, dL, dsw, elem) / (world if dL >= 64 else 1)  # this rank's slab
     achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
     kname = f"{dk}[L={dL},sweeps={dsw}]"
     traffic = None
@@ -295,21 +307,21 @@ def run_ours(args):
                 "avg_launch_ms": dom_ms, "algorithmic_bytes_per_launch": dom_bytes,
                 "share_of_step": dg["ms"] / total_prof, "peak_source": peak_src,
                 "frac_of_nominal_8000": achieved / NOMINAL_HBM_GBS}
-    aop = a_op_bytes(args.dim, args.size, elem)
-    v_gbs = aop / (ms_per_step * 1e-3) / 1e9
-    vcycle = {"a_op_bytes": aop, "effective_gbs": v_gbs, "frac_of_measured": v_gbs / peak,
+    aop = a_op_bytes(args.dim, gsize, elem)
+    v_gbs = aop / (ms_per_step * 1e-3) / 1e9 / world   # per GPU
+    vcycle = {"a_op_bytes": aop, "effective_gbs_per_gpu": v_gbs, "frac_of_measured": v_gbs / peak,
               "frac_of_nominal_8000": v_gbs / NOMINAL_HBM_GBS,
               "breakdown_ms": {f"{k}[L={L},sweeps={sw}]x{g['n']}": round(g["ms"], 4)
                                for (k, L, sw), g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])[:8]},
               "profiled_sum_ms": total_prof}
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timing
-    N = args.size ** args.dim
+    N = gsize ** args.dim // world   # points whose host buffers this rank moves
     dt = np.float64 if args.real == "double" else np.float32
     fh, ph = pkg.PinnedArray((N,), dt), pkg.PinnedArray((N,), dt)
     fh.array[...] = s.f.download().ravel()
     ph.array[...] = 0
-    ph.array[N // 2] = 1.0
+    ph.array[N // 2] = 1.0 if rank == world // 2 else 0.0
     s.step_host(fh.array, ph.array)  # warm
     barrier()
     ne2e = max(3, min(args.steps, 10))
@@ -322,8 +334,8 @@ def run_ours(args):
         t = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e = {"value": world / e2e_s, "unit": "V-cycles/s", "h2d_bytes_per_step": 2 * N * elem,
-           "d2h_bytes_per_step": N * elem + 8, "ms_per_step": e2e_s * 1e3, "steps": ne2e,
+    e2e = {"value": unit_scale / e2e_s, "unit": "V-cycles/s", "h2d_bytes_per_step": 2 * N * elem * world,
+           "d2h_bytes_per_step": (N * elem + 8) * world, "ms_per_step": e2e_s * 1e3, "steps": ne2e,
            "api": "mg_step_host (upload f, psi; psiOld<-psi; V-cycle; err; download psi)"}
     fh.free()
     ph.free()
@@ -350,7 +362,16 @@ def run_ours(args):
             "finite": finite,
         }
         if world > 1:
-            line["config"]["parallelism"] = f"{world} independent replicas (slab decomposition not built yet)"
+            si = s.slab_info()
+            line["config"].update({
+                "workload": f"{args.dim}D {gsize}^{args.dim} {dtype_name(args.real)} Poisson V-cycle cut into {world} z-slabs "
+                            f"({si['own_planes']} planes + {si['ghost']} ghost planes per side per GPU), NCCL send/recv halo "
+                            f"exchange before every smoother pass, levels below 64 replicated",
+                "baseline_config": "configs[3] (3D 1024^3 fp32 slab-decomposed across 2/4/8 B200)",
+                "grid": [gsize] * args.dim, "parallelism": f"z-slabs x{world}",
+                "unit": f"value counts V-cycles of the N=1 workload ({args.size}^{args.dim}); one {gsize}^{args.dim} V-cycle = {unit_scale:g} units",
+                "halo_exchanges_per_step": (si["exchanges"]) // max(1, args.steps + max(args.warmup, 3) + 5 + 1 + ne2e + 1),
+            })
         print(json.dumps(line))
     s.close()
     if dist is not None:
@@ -365,6 +386,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--dim", type=int, default=3)
     ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--mgpu-size", dest="mgpu_size", type=int, default=1024, help="global grid width for --gpus > 1")
     ap.add_argument("--real", default="float", choices=["float", "double", "float_acc64"])
     ap.add_argument("--tb", type=int, default=-1)
     ap.add_argument("--small-L", dest="small_L", type=int, default=-1)

@@ -418,7 +418,8 @@ int mg_profile_vcycle(mg_ctx *ctx, int cap, int *kind, int *L, int *sweeps, floa
     if (ctx->mode != MG_MODE_FUSED) return ctx->fail(MG_ESTATE, "mg_profile_vcycle: fused mode only");
     ctx->prof.clear();
     ctx->prof_on = true;
-    int rc = ctx->eng->twogrid_fused(ctx, 1.0 / ctx->size, ctx->psi, ctx->f, ctx->nlevels - 1);
+    int rc = ctx->group ? ctx->eng->slab_vcycle(ctx->group)
+                        : ctx->eng->twogrid_fused(ctx, 1.0 / ctx->size, ctx->psi, ctx->f, ctx->nlevels - 1);
     ctx->prof_on = false;
     cudaError_t e = cudaStreamSynchronize(ctx->stream);
     int cnt = 0;
