@@ -55,11 +55,12 @@ struct Engine;
 struct mg_ctx {
     int dim = 0, size = 0, real_kind = 0, smooth = 7, device = 0, nlevels = 0, rank = 0, nranks = 1;
     size_t elem = 0, N = 0;
-    int mode = MG_MODE_FUSED, tb = 1, small_L = 0, use_graph = 1;
+    int mode = MG_MODE_FUSED, tb = 4, small_L = 0, use_graph = 1;
     int tb2 = 7;             // 2-D: sweeps per pass of the warp-streaming smoother (0 = untiled)
     int warp2d_min_L = 128;  // 2-D: smallest level width handled by the warp-streaming smoother
     int ty_override = 0;     // 2-D: rows per warp work item (0 = cost model)
     int stream_min_L = 128;  // smallest level width handled by the streaming (TMA) smoother
+    int num_sms = 148;       // SM count of the device (queried at init)
     int stream_flags = 0;    // debug switches of the streaming smoother (see Stream3DArgs::flags)
     int tz_override = 0;     // planes per CTA of the streaming smoother (0 = cost model)
     // TMA descriptors of the source fields, keyed by (pointer, level width, box x, box y)
@@ -340,21 +341,40 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         const int nown = nz_hi - nz_lo;
         auto kern = k_stream3d<R, A, S, PRO, RES, TX, TY>;
         MG_CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-        // planes per CTA: minimise waves x steps-per-CTA on 148 SMs (one CTA per SM)
-        int TZ = c->tz_override;
-        if (TZ <= 0) {
-            const long tiles = (long)((L + TX - 1) / TX) * ((L + TY - 1) / TY);
+        // One CTA per SM, each given an equal share of the tile x plane-pair work (balanced
+        // persistent partition inside the kernel); "tz" asks for ~tz planes per share instead.
+        const long tiles = (long)((L + TX - 1) / TX) * ((L + TY - 1) / TY);
+        const long work = tiles * nown;                    // tile-planes
+        int occ = 1;   // resident CTAs per SM (shared memory / registers decide; 1 for S >= 3)
+        MG_CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        MG_CK(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, C::NTHREADS, C::SMEM_BYTES));
+        if (occ < 1) occ = 1;
+        long ncta;
+        if (c->tz_override > 0) {
+            ncta = (work + c->tz_override - 1) / c->tz_override;
+        } else if (S <= 2) {
+            // Shallow passes are HBM-bound: keep whole tile columns marching through z in lock
+            // step, so that the halo rows neighbouring tiles share are still in L2 when the
+            // neighbour reads them. Columns are cut into nz equal chunks by a small cost model
+            // (waves x planes streamed per CTA).
             long best = -1;
+            ncta = tiles;
             for (int cand = nown; cand >= 8; cand >>= 1) {
-                long ncta = tiles * ((nown + cand - 1) / cand);
-                long cost = ((ncta + 147) / 148) * (cand + 3 * C::H);
-                if (best < 0 || cost < best) { best = cost; TZ = cand; }
+                const long n = tiles * ((nown + cand - 1) / cand);
+                const long cost = ((n + (long)c->num_sms * occ - 1) / ((long)c->num_sms * occ)) * (cand + 3 * C::H);
+                if (best < 0 || cost < best) { best = cost; ncta = n; }
             }
+        } else {
+            // Deep passes are issue-bound: equal shares of the tile x plane work for every
+            // resident CTA (a share may span two tile columns), no tail wave.
+            ncta = (long)c->num_sms * occ;
+            const long min_planes = 16;  // below this the 3*NST fill/drain steps dominate
+            if (ncta > (work + min_planes - 1) / min_planes) ncta = (work + min_planes - 1) / min_planes;
         }
-        if (TZ > nown) TZ = nown;
-        TZ &= ~1;
-        dim3 grid((L + TX - 1) / TX, (L + TY - 1) / TY, (nown + TZ - 1) / TZ);
-        Stream3DArgs<R> a{dst, Vp, Rout, L, TZ, c->stream_flags, nz_lo, nz_hi, zdom0, zdom0 + L, rz_off, vz_off};
+        if (ncta < 1) ncta = 1;
+        if (ncta > work / 2) ncta = work / 2 > 0 ? work / 2 : 1;
+        dim3 grid((unsigned)ncta, 1, 1);
+        Stream3DArgs<R> a{dst, Vp, Rout, L, 0, c->stream_flags, nz_lo, nz_hi, zdom0, zdom0 + L, rz_off, vz_off};
         c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : (RES ? MG_K_SWEEP_RESTRICT : MG_K_SWEEP), L, S);
         kern<<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(*map, *fmap, a, cf);
         c->prof_end();
@@ -800,6 +820,7 @@ inline int mg_ctx::init(int dim_, int size_, int real_kind_, int smooth_, int de
     if (device_ < 0) MG_CK(this, cudaGetDevice(&device_));
     device = device_;
     MG_CK(this, cudaSetDevice(device));
+    MG_CK(this, cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, device));
     MG_CK(this, cudaStreamCreateWithFlags(&own_stream, cudaStreamNonBlocking));
     MG_CK(this, cudaStreamCreateWithFlags(&cap_stream, cudaStreamNonBlocking));
     stream = own_stream;

@@ -54,6 +54,10 @@ __device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
 {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
 }
+__device__ __forceinline__ void mbar_inval(uint64_t *bar)
+{
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_fence_init()
 {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -139,7 +143,7 @@ template <typename R> struct Stream3DArgs {
     const R *Vp;      // PRO: coarse correction Vs[L/2]
     R *Rout;          // RES: Rs[L/2]
     int L;            // level width
-    int TZ;           // planes per CTA (even)
+    int TZ;           // unused (kept for ABI stability of the args block)
     int flags;        // debug: bit 0 = never take the steady-state body, bit 1 = always mask
     // slab view (multi-GPU): the arrays hold planes [0, nplanes) of which [nz_lo, nz_hi) are
     // owned (written) by this rank; the global grid occupies local planes [zdom0, zdom1).
@@ -174,9 +178,12 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     const bool worker = tid < C::NT;   // the last warp's spare threads mirror unit 0 and never store
     const int ux = worker ? tid % C::UX : 0, uy = worker ? tid / C::UX : 0;
     const int L = a.L;
-    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY, z0 = a.nz_lo + blockIdx.z * a.TZ;
-    const int z1 = min(z0 + a.TZ, a.nz_hi);
     const int zdom0 = a.zdom0, zdom1 = a.zdom1;
+    bool first_chunk = true;
+
+    // One chunk = tile (x0, y0) streamed through the owned planes [z0, z1). A CTA may process
+    // several chunks (balanced persistent partition, see the end of the kernel).
+    auto run_chunk = [&](const int x0, const int y0, const int z0, const int z1) {
     const int TZ = z1 - z0;
     const int zb = z0 - H;          // plane index of input step 0
     const int nin = TZ + 2 * H;     // input planes
@@ -203,13 +210,16 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     // the whole (tile + halo) footprint lies inside the grid in x and y: no in-plane masking
     const bool cta_inner = (x0 - C::HX >= 0) && (x0 + TX + C::HX <= L) && (y0 - C::HY >= 0) && (y0 + TY + C::HY <= L);
 
+    __syncthreads();  // every thread is done with the previous chunk's shared memory
     if (tid == 0) {
 #pragma unroll
-        for (int k = 0; k < NSLOT; ++k) mbar_init(&mbar_u[k], 1);
-#pragma unroll
-        for (int k = 0; k < NF; ++k) mbar_init(&mbar_f[k], 1);
+        for (int k = 0; k < NSLOT + NF; ++k) {
+            if (!first_chunk) mbar_inval(&mbar_u[k]);   // all of its transfers were awaited
+            mbar_init(&mbar_u[k], 1);                   // mbar_f follows mbar_u in memory
+        }
         mbar_fence_init();
     }
+    first_chunk = false;
     __syncthreads();
     if (tid == 0) {
 #pragma unroll
@@ -226,26 +236,38 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         tma_load_3d(f_slot(0), &f_map, x0 - C::HX, y0 - C::HY, zb, &mbar_f[0]);
     }
 
-    // PRO: add prolong(V) to the own points of an arrived source slot, in place
-    auto fixup = [&](int t, int slot) {
-        if (!PRO || !worker) return;
+    // PRO: add prolong(V) to the own points of an arrived source slot, in place. The coarse
+    // values are fetched at the START of the step (fix_load) and applied at its end (fix_apply),
+    // so their global-memory latency hides behind the step's stage work.
+    R vpre[2][VX / 2 > 0 ? VX / 2 : 1];
+    bool vpre_on = false;
+    auto fix_load = [&](int t) {
+        vpre_on = false;
+        if (!PRO) return;
         const int p = zb + t;
         if (p < zdom0 || p >= zdom1) return;                       // plane outside the grid stays 0
+        vpre_on = true;
         const int pc = ((p - zdom0) >> 1) + a.vz_off;              // coarse plane (local index)
-        R *sl = in_slot(slot);
         const int L2 = L >> 1;
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const bool in = r == 0 ? in0 : in1;
-            if (!in) continue;
             const size_t crow = (size_t)(gx0 >> 1) + (size_t)L2 * ((size_t)((gy0 + r) >> 1) + (size_t)L2 * (size_t)pc);
+#pragma unroll
+            for (int i = 0; i < VX / 2; ++i) vpre[r][i] = in ? a.Vp[crow + i] : (R)0;
+        }
+    };
+    auto fix_apply = [&](int slot) {
+        if (!PRO || !vpre_on) return;
+        R *sl = in_slot(slot);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const bool in = r == 0 ? in0 : in1;
+            if (!in) continue;
             R u[VX];
             Vec<R>::unpack(*(const VT *)(sl + (r == 0 ? off0 : off1)), u);
 #pragma unroll
-            for (int i = 0; i < VX; ++i) {
-                R vv = a.Vp[crow + (i >> 1)];
-                u[i] = (R)Ar<A>::add((A)u[i], (A)vv);
-            }
+            for (int i = 0; i < VX; ++i) u[i] = (R)Ar<A>::add((A)u[i], (A)vpre[r][i >> 1]);
             *(VT *)(sl + (r == 0 ? off0 : off1)) = Vec<R>::pack(u);
         }
     };
@@ -260,8 +282,9 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     for (int i = 0; i < VX / 2; ++i) rpart[i] = (A)0;
 
     if (PRO) {
+        fix_load(0);
         mbar_wait(&mbar_u[0], 0);
-        fixup(0, 0);
+        fix_apply(0);
         __syncthreads();
     }
 
@@ -291,6 +314,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                 tma_load_3d(f_slot(ksf), &f_map, x0 - C::HX, y0 - C::HY, zb + j, &mbar_f[ksf]);
             }
         }
+        if (PRO && t + 1 < nin) fix_load(t + 1);
         // (2) source plane of this step (PRO: it was awaited and fixed up during step t-1)
         if (!PRO) {
             if (ST || t < nin) mbar_wait(&mbar_u[su], (uint32_t)pu);
@@ -419,7 +443,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         if (PRO && t + 1 < nin) {
             const int sn = su + 1 == NSLOT ? 0 : su + 1;
             mbar_wait(&mbar_u[sn], (uint32_t)(sn == 0 ? pu ^ 1 : pu));
-            fixup(t + 1, sn);
+            fix_apply(sn);
         }
         __syncthreads();
         // advance the ring cursors
@@ -452,6 +476,24 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
             const int ta = phase == 0 ? 0 : t_hi + 1, tb = phase == 0 ? min(t_lo, T) : T;
 #pragma unroll 1
             for (int t = ta; t < tb; ++t) step(std::false_type{}, std::true_type{}, t);
+        }
+    }
+    };  // run_chunk
+
+    // Balanced persistent partition: the launch is ntiles x (owned planes / 2) plane pairs of
+    // work, dealt out in equal contiguous shares to the gridDim.x CTAs (one per SM). A share
+    // may end one tile column and begin the next; each piece is a chunk with its own halo.
+    {
+        const int ntx = (L + TX - 1) / TX, nty = (L + TY - 1) / TY;
+        const long long npair = (a.nz_hi - a.nz_lo) >> 1;
+        const long long W2 = (long long)ntx * nty * npair;
+        long long lo = W2 * blockIdx.x / gridDim.x;
+        const long long hi = W2 * (blockIdx.x + 1) / gridDim.x;
+        while (lo < hi) {
+            const long long tile = lo / npair, zp = lo - tile * npair;
+            const long long n = min(npair - zp, hi - lo);
+            run_chunk((int)(tile % ntx) * TX, (int)(tile / ntx) * TY, a.nz_lo + 2 * (int)zp, a.nz_lo + 2 * (int)(zp + n));
+            lo += n;
         }
     }
 }
