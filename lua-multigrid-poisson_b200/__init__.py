@@ -485,3 +485,48 @@ def slab_partition(size, nranks):
         levels.append(dict(L=L, distributed=d, planes_per_rank=L // nranks if d else L, ghost=4 if d else 0))
         L //= 2
     return levels
+
+
+def plan_passes(n, tb, has_res):
+    """Host mirror of EngineT::plan_passes (csrc/mg_engine.cuh): how n Jacobi sweeps are split
+    into smoother passes of <= tb sweeps; with a fused residual stage the last pass has <= 3."""
+    plan, rem, last = [], n, 0
+    if has_res:
+        last = min(n, 3, tb)
+        rem = n - last
+    if rem > 0:
+        k = (rem + tb - 1) // tb
+        base, extra = divmod(rem, k)
+        plan += [base + (1 if i < extra else 0) for i in range(k)]
+    if has_res:
+        plan.append(last)
+    return plan
+
+
+def slab_schedule(size, nranks, smooth=7, tb=4):
+    """The communication schedule of one slab V-cycle (csrc/mg_engine.cuh::slab_twogrid), as a
+    list of (op, level width, detail) tuples: what is exchanged, to which depth, and when."""
+    ops = []
+
+    def visit(L):
+        lv = [x for x in slab_partition(size, nranks) if x["L"] == L][0]
+        if not lv["distributed"]:
+            ops.append(("replicated_vcycle", L, None))
+            return
+        coarse = [x for x in slab_partition(size, nranks) if x["L"] == L // 2][0]
+        pre = plan_passes(smooth, tb, True)
+        for i, s in enumerate(pre):
+            res = i == len(pre) - 1
+            ops.append(("exchange_u", L, s + (1 if res else 0)))
+            ops.append(("pass", L, dict(sweeps=s, res=res, pro=False)))
+        ops.append(("exchange_R" if coarse["distributed"] else "allgather_R", L // 2, 4 if coarse["distributed"] else None))
+        visit(L // 2)
+        if coarse["distributed"]:
+            ops.append(("exchange_V", L // 2, 2))
+        for i, s in enumerate(plan_passes(smooth, tb, False)):
+            ops.append(("exchange_u", L, s))
+            ops.append(("pass", L, dict(sweeps=s, res=False, pro=i == 0)))
+
+    ops.append(("exchange_f", size, 4))
+    visit(size)
+    return ops
