@@ -110,6 +110,7 @@ int mg_set_option(mg_ctx *ctx, const char *name, int value)
     else if (n == "stream_min_L") ctx->stream_min_L = value < 64 ? 64 : value;
     else if (n == "tz") ctx->tz_override = value;
     else if (n == "stream_flags") ctx->stream_flags = value;
+    else if (n == "tma_promo") { ctx->tma_promo = value; ctx->tmaps.clear(); }
     else if (n == "tb2") { if (value < 0 || value > 7) return ctx->fail(MG_EINVAL, "tb2 must be 0..7"); ctx->tb2 = value; }
     else if (n == "warp2d_min_L") ctx->warp2d_min_L = value < 32 ? 32 : value;
     else if (n == "ty") ctx->ty_override = value;

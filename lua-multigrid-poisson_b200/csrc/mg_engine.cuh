@@ -61,6 +61,7 @@ struct mg_ctx {
     int ty_override = 0;     // 2-D: rows per warp work item (0 = cost model)
     int stream_min_L = 128;  // smallest level width handled by the streaming (TMA) smoother
     int num_sms = 148;       // SM count of the device (queried at init)
+    int tma_promo = 3;       // L2 promotion of the TMA descriptors: 0 none, 1 64 B, 2 128 B, 3 256 B
     int stream_flags = 0;    // debug switches of the streaming smoother (see Stream3DArgs::flags)
     int tz_override = 0;     // planes per CTA of the streaming smoother (0 = cost model)
     // TMA descriptors of the source fields, keyed by (pointer, level width, box x, box y)
@@ -322,8 +323,15 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
     int launch_stream3d(mg_ctx *c, int lv, R *dst, const R *src, const R *f, const R *Vp, R *Rout, const Coef<A> &cf)
     {
         const int L = 1 << lv;
-        // in-plane tile: 64 x 32 for 4-byte reals, 32 x 32 for 8-byte reals (shared-memory budget)
-        constexpr int TX = sizeof(R) == 4 ? 64 : 32, TY = 32;
+        // In-plane tile. 4-byte reals: 88 x 24 (+ halo = 96 x 32): 24 vectors per row and a 384-byte
+        // row pitch, so every quarter-warp of a 128-bit shared-memory access stays inside one row
+        // and is bank-conflict free; tiles need not divide the grid (balanced partition + masks).
+        // 8-byte reals: 32 x 32 (shared-memory budget).
+#ifndef MG_TILE_X
+#define MG_TILE_X 88
+#define MG_TILE_Y 24
+#endif
+        constexpr int TX = sizeof(R) == 4 ? MG_TILE_X : 32, TY = sizeof(R) == 4 ? MG_TILE_Y : 32;
         typedef Stream3DCfg<R, S, RES, TX, TY> C;
         const CUtensorMap *map = nullptr, *fmap = nullptr;
         const int nplanes = c->planes(lv);
@@ -982,7 +990,11 @@ inline int mg_ctx::tensor_map(const void *base, int L, int nplanes, int box_x, i
     cuuint32_t est[3] = {1, 1, 1};
     CUresult r = encode(&m, elem == 8 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT64 : CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3,
                         const_cast<void *>(base), gdim, gstr, box, est, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                        CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                        CU_TENSOR_MAP_SWIZZLE_NONE,
+                        tma_promo == 0 ? CU_TENSOR_MAP_L2_PROMOTION_NONE
+                                       : (tma_promo == 1 ? CU_TENSOR_MAP_L2_PROMOTION_L2_64B
+                                                         : (tma_promo == 2 ? CU_TENSOR_MAP_L2_PROMOTION_L2_128B
+                                                                           : CU_TENSOR_MAP_L2_PROMOTION_L2_256B)),
                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         err = "cuTensorMapEncodeTiled failed with CUresult " + std::to_string((int)r);

@@ -35,7 +35,7 @@
 #include "mg_math.cuh"
 
 #ifndef MG_STREAM_SHFL
-#define MG_STREAM_SHFL 0      // x-neighbours across units via warp shuffle (0: 4-byte shared loads)
+#define MG_STREAM_SHFL 1      // x-neighbours across units via warp shuffle (0: 4-byte shared loads)
 #endif
 #ifndef MG_STEADY_UNROLL
 #define MG_STEADY_UNROLL 2    // unroll factor of the steady-state step loop
@@ -95,6 +95,20 @@ __device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *m
         " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(smem_dst)),
         "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
         : "memory");
+}
+
+// predicated shared-memory load: returns *p if pred, else old (no branch, no access when !pred)
+__device__ __forceinline__ float lds_if(bool pred, const float *p, float old)
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.shared.f32 %0, [%1];\n}\n"
+                 : "+f"(old) : "r"(smem_u32(p)), "r"((unsigned)pred) : "memory");
+    return old;
+}
+__device__ __forceinline__ double lds_if(bool pred, const double *p, double old)
+{
+    asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.shared.f64 %0, [%1];\n}\n"
+                 : "+d"(old) : "r"(smem_u32(p)), "r"((unsigned)pred) : "memory");
+    return old;
 }
 
 // ------------------------------------------------------------------ vector access
@@ -360,8 +374,9 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
             if (MG_STREAM_SHFL) {
                 l0 = __shfl_up_sync(0xffffffffu, c0[VX - 1], 1); l1 = __shfl_up_sync(0xffffffffu, c1[VX - 1], 1);
                 r0 = __shfl_down_sync(0xffffffffu, c0[0], 1); r1 = __shfl_down_sync(0xffffffffu, c1[0], 1);
-                if (lane == 0) { l0 = in[off0 + dl]; l1 = in[off1 + dl]; }
-                if (lane == 31) { r0 = in[off0 + dr]; r1 = in[off1 + dr]; }
+                // lanes 0 / 31 have no such lane: one-lane predicated loads, no branch
+                l0 = lds_if(lane == 0, in + off0 + dl, l0); l1 = lds_if(lane == 0, in + off1 + dl, l1);
+                r0 = lds_if(lane == 31, in + off0 + dr, r0); r1 = lds_if(lane == 31, in + off1 + dr, r1);
             } else {
                 l0 = in[off0 + dl]; l1 = in[off1 + dl]; r0 = in[off0 + dr]; r1 = in[off1 + dr];
             }
