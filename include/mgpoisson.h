@@ -84,7 +84,7 @@ int mg_set_stream(mg_ctx *ctx, void *cuda_stream);   /* borrow a cudaStream_t (N
 int mg_set_tuning(mg_ctx *ctx, int tb, int small_L, int use_graph);
 /* named integer options: "tb", "small_L", "graph", "stream_min_L" (smallest level width
  * given to the streaming smoother), "tz" (planes per CTA of the streaming smoother; 0 = auto), "tb2" (2-D: sweeps per pass of the
- * warp-streaming smoother, 0..7), "warp2d_min_L", "ty" (2-D: rows per warp work item) */
+ * warp-streaming smoother, 0..7), "warp2d_min_L", "ty" (2-D: rows per warp work item), "slab_p2p" (see below), "tma_promo" */
 int mg_set_option(mg_ctx *ctx, const char *name, int value);
 int mg_get_info(mg_ctx *ctx, int *dim, int *size, int *real_kind, int *smooth, int *nlevels,
                 uint64_t *arena_bytes);
@@ -160,6 +160,13 @@ int mg_nccl_unique_id(void *id, size_t bytes);
 int mg_create_slab(int dim, int size, int real_kind, int smooth, int device, int rank, int nranks,
                    const void *nccl_id, size_t id_bytes, mg_ctx **out);
 int mg_create_slab_local(int dim, int size, int real_kind, int smooth, int device, int nslabs, mg_ctx **out);
+/* Fused halo exchange: every rank exports the CUDA IPC handle of its arena (64 bytes); after an
+ * all-gather each rank attaches its two neighbours. From then on the smoother kernel that
+ * produces a boundary plane stores it straight into the neighbour's ghost planes over NVLink,
+ * and the only inter-GPU operation per pass is a flag handshake (option "slab_p2p" = 0 goes
+ * back to ncclSend/ncclRecv). mg_create_slab_local uses the same path with plain pointers. */
+int mg_slab_ipc_export(mg_ctx *ctx, void *handle, size_t bytes);
+int mg_slab_ipc_attach(mg_ctx *ctx, const void *handles, size_t bytes);
 int mg_slab_info(mg_ctx *ctx, int *rank, int *nranks, int *own_planes, int *ghost, uint64_t *exchanges,
                  uint64_t *exchanged_bytes);
 /* MGPOISSON_CDEF_END */

@@ -124,6 +124,8 @@ def lib():
         "mg_nccl_unique_id": (i, [vp, sz]),
         "mg_create_slab": (i, [i, i, i, i, i, i, i, vp, sz, C.POINTER(vp)]),
         "mg_create_slab_local": (i, [i, i, i, i, i, i, C.POINTER(vp)]),
+        "mg_slab_ipc_export": (i, [vp, vp, sz]),
+        "mg_slab_ipc_attach": (i, [vp, vp, sz]),
         "mg_slab_info": (i, [vp, pi, pi, pi, pi, C.POINTER(u64), C.POINTER(u64)]),
     }
     for name, (res, args) in sig.items():
@@ -457,7 +459,7 @@ def nccl_unique_id() -> bytes:
     return buf.raw
 
 
-def create_distributed(size, real="float", dim=3, smooth=None, out=False):
+def create_distributed(size, real="float", dim=3, smooth=None, out=False, p2p=True):
     """One slab per process (torchrun: one process per GPU). torch.distributed is only the
     plumbing that ships rank 0's NCCL unique id to the other ranks; every halo exchange,
     all-gather and reduction afterwards is issued by libmgpoisson on its own communicator."""
@@ -472,8 +474,19 @@ def create_distributed(size, real="float", dim=3, smooth=None, out=False):
         t = torch.frombuffer(bytearray(nccl_unique_id()), dtype=torch.uint8).to(dev)
     dist.broadcast(t, 0)
     nid = bytes(t.cpu().numpy().tobytes())
-    return MultigridCUDA(size, real, dim=dim, smooth=smooth, out=out, device=torch.cuda.current_device(),
-                         slab=(rank, world, nid))
+    s = MultigridCUDA(size, real, dim=dim, smooth=smooth, out=out, device=torch.cuda.current_device(),
+                      slab=(rank, world, nid))
+    if p2p:
+        # fused halo exchange: all-gather the CUDA IPC handles of the arenas, map the neighbours
+        hbuf = C.create_string_buffer(64)
+        s._ck(lib().mg_slab_ipc_export(s._h, hbuf, 64))
+        mine = torch.frombuffer(bytearray(hbuf.raw), dtype=torch.uint8).to(dev)
+        allh = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(allh, mine)
+        blob = b"".join(bytes(x.cpu().numpy().tobytes()) for x in allh)
+        s._ck(lib().mg_slab_ipc_attach(s._h, C.create_string_buffer(blob, len(blob)), len(blob)))
+        dist.barrier()
+    return s
 
 
 def slab_partition(size, nranks):

@@ -110,6 +110,13 @@ int mg_set_option(mg_ctx *ctx, const char *name, int value)
     else if (n == "stream_min_L") ctx->stream_min_L = value < 64 ? 64 : value;
     else if (n == "tz") ctx->tz_override = value;
     else if (n == "stream_flags") ctx->stream_flags = value;
+    else if (n == "slab_p2p") {   // 0: halo planes by ncclSend/ncclRecv (or memcpy), 1: fused peer stores
+        for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) {
+            if (value && !(m->peer_lo || m->peer_hi)) return ctx->fail(MG_ESTATE, "slab_p2p: no peer mapped");
+            m->p2p = value != 0;
+            m->u_ghost_dirty = m->f_ghost_dirty = true;
+        }
+    }
     else if (n == "tma_promo") { ctx->tma_promo = value; ctx->tmaps.clear(); }
     else if (n == "tb2") { if (value < 0 || value > 7) return ctx->fail(MG_EINVAL, "tb2 must be 0..7"); ctx->tb2 = value; }
     else if (n == "warp2d_min_L") ctx->warp2d_min_L = value < 32 ? 32 : value;
@@ -504,7 +511,47 @@ int mg_create_slab_local(int dim, int size, int real_kind, int smooth, int devic
         g->m.push_back(c);
     }
     g->m[0]->owns_group = true;
+    for (int r = 0; r < nslabs; ++r) {  // same process: the neighbours' arenas are directly addressable
+        mg_ctx *c = g->m[r];
+        c->peer_lo = r > 0 ? (char *)g->m[r - 1]->arena : nullptr;
+        c->peer_hi = r < nslabs - 1 ? (char *)g->m[r + 1]->arena : nullptr;
+        c->p2p = true;
+    }
     *out = g->m[0];
+    return MG_OK;
+}
+
+// CUDA IPC handle of this rank's arena (64 bytes), to be shipped to its two neighbours
+int mg_slab_ipc_export(mg_ctx *ctx, void *handle, size_t bytes)
+{
+    CTX_OR_FAIL(ctx);
+    if (!handle || bytes < sizeof(cudaIpcMemHandle_t)) return ctx->fail(MG_EINVAL, "mg_slab_ipc_export: need 64 bytes");
+    cudaIpcMemHandle_t h;
+    MG_CK(ctx, cudaIpcGetMemHandle(&h, ctx->arena));
+    memcpy(handle, &h, sizeof(h));
+    return MG_OK;
+}
+
+// handles = nranks x 64 bytes, indexed by rank (e.g. the result of an all-gather). Maps the two
+// neighbours' arenas and switches the handle to the fused halo exchange. Every rank must have
+// attached (barrier) before the next V-cycle.
+int mg_slab_ipc_attach(mg_ctx *ctx, const void *handles, size_t bytes)
+{
+    CTX_OR_FAIL(ctx);
+    if (!ctx->group || !ctx->group->nccl) return ctx->fail(MG_ESTATE, "mg_slab_ipc_attach: not a multi-process slab");
+    if (!handles || bytes < (size_t)ctx->nranks * sizeof(cudaIpcMemHandle_t)) return ctx->fail(MG_EINVAL, "mg_slab_ipc_attach: short buffer");
+    const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)handles;
+    if (ctx->rank > 0) {
+        cudaIpcMemHandle_t hh; memcpy(&hh, &h[ctx->rank - 1], sizeof(hh));
+        MG_CK(ctx, cudaIpcOpenMemHandle((void **)&ctx->peer_lo, hh, cudaIpcMemLazyEnablePeerAccess));
+    }
+    if (ctx->rank < ctx->nranks - 1) {
+        cudaIpcMemHandle_t hh; memcpy(&hh, &h[ctx->rank + 1], sizeof(hh));
+        MG_CK(ctx, cudaIpcOpenMemHandle((void **)&ctx->peer_hi, hh, cudaIpcMemLazyEnablePeerAccess));
+    }
+    ctx->peer_ipc = true;
+    ctx->p2p = true;
+    ctx->u_ghost_dirty = ctx->f_ghost_dirty = true;
     return MG_OK;
 }
 

@@ -24,6 +24,37 @@ namespace mg {
 
 constexpr int MAX_LEVELS = 24;
 constexpr size_t ARENA_ALIGN = 1024;
+constexpr size_t ARENA_HEADER = 1024;   // pass counter + the two neighbour flags of the slab handshake
+
+// Handshake of the fused halo exchange (one process per GPU): words 0 / 16 / 32 of the arena are
+// this rank's pass counter and the counters its lower / upper neighbour last published.
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+// before pass n+1: both neighbours must have finished their pass n (their stores into our ghost
+// planes are complete, and they no longer read the ghost planes we are about to overwrite)
+__global__ void k_slab_wait(const unsigned long long *hdr, int has_lo, int has_hi)
+{
+    const unsigned long long n = hdr[0];
+    if (has_lo) while (ld_acquire_sys(hdr + 16) < n) { }
+    if (has_hi) while (ld_acquire_sys(hdr + 32) < n) { }
+}
+// after pass n+1: publish n+1 to both neighbours (the kernel boundary ordered our peer stores)
+__global__ void k_slab_signal(unsigned long long *hdr, unsigned long long *lo_hdr, unsigned long long *hi_hdr)
+{
+    const unsigned long long n = hdr[0] + 1;
+    hdr[0] = n;
+    __threadfence_system();
+    if (lo_hdr) st_release_sys(lo_hdr + 32, n);   // we are the lower neighbour's UPPER neighbour
+    if (hi_hdr) st_release_sys(hi_hdr + 16, n);   // and the upper neighbour's LOWER neighbour
+}
 
 struct TraceRec {
     char name;
@@ -106,7 +137,11 @@ struct mg_ctx {
     bool dist[mg::MAX_LEVELS] = {};     // level is cut across the ranks
     int nzl[mg::MAX_LEVELS] = {};       // planes owned by each rank at a distributed level
     mg::SlabGroup *group = nullptr;
-    bool owns_group = false, f_ghost_dirty = true;
+    bool owns_group = false, f_ghost_dirty = true, u_ghost_dirty = true;
+    // fused halo exchange over peer memory: the neighbours' arenas (same layout as ours), mapped
+    // with CUDA IPC (other process) or simply their pointers (same process). p2p = use them.
+    char *peer_lo = nullptr, *peer_hi = nullptr;
+    bool peer_ipc = false, p2p = false;
     size_t Ntop = 0;                    // elements allocated for a top-level field (incl. ghosts)
 
     int planes(int lv) const { return dist[lv] ? nzl[lv] + 2 * G : (dim == 3 ? (1 << lv) : 1); }
@@ -221,7 +256,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         }
         k_init_cells<R, A, DIM><<<g, b, 0, c->stream>>>((R *)c->f, (R *)c->psi, c->size, plane0, k0);
         MG_LAUNCH_CHECK(c);
-        c->f_ghost_dirty = true;
+        c->f_ghost_dirty = c->u_ghost_dirty = true;
         return MG_OK;
     }
     int jacobi(mg_ctx *c, int L, void *dest, const void *u, const void *f, double h) override
@@ -382,7 +417,18 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         if (ncta < 1) ncta = 1;
         if (ncta > work / 2) ncta = work / 2 > 0 ? work / 2 : 1;
         dim3 grid((unsigned)ncta, 1, 1);
-        Stream3DArgs<R> a{dst, Vp, Rout, L, 0, c->stream_flags, nz_lo, nz_hi, zdom0, zdom0 + L, rz_off, vz_off};
+        Stream3DArgs<R> a{dst, Vp, Rout, L, 0, c->stream_flags, nz_lo, nz_hi, zdom0, zdom0 + L, rz_off, vz_off,
+                          nullptr, nullptr, nullptr, nullptr, c->G};
+        if (c->dist[lv] && c->p2p) {  // fused halo exchange: same offsets inside the neighbours' arenas
+            const size_t doff = c->arena_off(dst);
+            if (c->peer_lo) a.peer_lo = (R *)(c->peer_lo + doff);
+            if (c->peer_hi) a.peer_hi = (R *)(c->peer_hi + doff);
+            if (Rout && c->dist[lv - 1]) {
+                const size_t roff = c->arena_off(Rout);
+                if (c->peer_lo) a.rpeer_lo = (R *)(c->peer_lo + roff);
+                if (c->peer_hi) a.rpeer_hi = (R *)(c->peer_hi + roff);
+            }
+        }
         c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : (RES ? MG_K_SWEEP_RESTRICT : MG_K_SWEEP), L, S);
         kern<<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(*map, *fmap, a, cf);
         c->prof_end();
@@ -433,9 +479,29 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
 
     // ---- slab V-cycle (mg_slab.cuh): the same schedule on every rank, halo planes in between
     static char *at(mg_ctx *c, size_t off) { return (char *)c->arena + off; }
-    int slab_exchange(SlabGroup *g, size_t off, int lv, int depth)
+    // handshake around a pass of the fused-exchange mode (only needed across processes; slabs of
+    // one process share a stream, which already orders them)
+    int slab_wait(SlabGroup *g)
+    {
+        mg_ctx *c = g->m[0];
+        if (!c->p2p || !g->nccl) return MG_OK;
+        k_slab_wait<<<1, 1, 0, c->stream>>>((const unsigned long long *)c->arena, c->peer_lo != nullptr, c->peer_hi != nullptr);
+        MG_LAUNCH_CHECK(c);
+        return MG_OK;
+    }
+    int slab_signal(SlabGroup *g)
+    {
+        mg_ctx *c = g->m[0];
+        if (!c->p2p || !g->nccl) return MG_OK;
+        k_slab_signal<<<1, 1, 0, c->stream>>>((unsigned long long *)c->arena, (unsigned long long *)c->peer_lo,
+                                              (unsigned long long *)c->peer_hi);
+        MG_LAUNCH_CHECK(c);
+        return MG_OK;
+    }
+    int slab_exchange(SlabGroup *g, size_t off, int lv, int depth, bool force = false)
     {
         mg_ctx *c0 = g->m[0];
+        if (c0->p2p && !force) return MG_OK;   // the producing kernel already stored the ghosts
         const size_t pb = c0->plane_elems(lv) * c0->elem;
         const int G = c0->G, nz = c0->nzl[lv];
         const size_t nb = (size_t)depth * pb;
@@ -508,10 +574,12 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             for (int i = 0; i < np; ++i) {
                 const bool res = i == np - 1;
                 if ((rc = slab_exchange(g, cur, lv, plan[i] + (res ? 1 : 0)))) return rc;
+                if ((rc = slab_wait(g))) return rc;
                 for (mg_ctx *c : g->m)
                     if ((rc = stream3d_pass(c, lv, plan[i], false, res, (R *)at(c, oth), (const R *)at(c, cur),
                                             (const R *)at(c, f_off), nullptr, res ? (R *)at(c, Rc_off) : nullptr, cf)))
                         return rc;
+                if ((rc = slab_signal(g))) return rc;
                 size_t t = cur; cur = oth; oth = t;
             }
             // the restricted residual is the next level's right-hand side
@@ -524,10 +592,12 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             np = plan_passes(c0->smooth, c0->tb, false, plan);
             for (int i = 0; i < np; ++i) {
                 if ((rc = slab_exchange(g, cur, lv, plan[i]))) return rc;
+                if ((rc = slab_wait(g))) return rc;
                 for (mg_ctx *c : g->m)
                     if ((rc = stream3d_pass(c, lv, plan[i], i == 0, false, (R *)at(c, oth), (const R *)at(c, cur),
                                             (const R *)at(c, f_off), i == 0 ? (const R *)at(c, Vc_off) : nullptr, nullptr, cf)))
                         return rc;
+                if ((rc = slab_signal(g))) return rc;
                 size_t t = cur; cur = oth; oth = t;
             }
             if (cur != u_off)
@@ -543,9 +613,14 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         mg_ctx *c0 = g->m[0];
         const int top = c0->nlevels - 1;
         if (c0->f_ghost_dirty) {  // f is static between uploads: its ghosts are exchanged once
-            int rc = slab_exchange(g, c0->arena_off(c0->f), top, c0->G);
+            int rc = slab_exchange(g, c0->arena_off(c0->f), top, c0->G, true);
             if (rc) return rc;
             for (mg_ctx *c : g->m) c->f_ghost_dirty = false;
+        }
+        if (c0->u_ghost_dirty && c0->p2p) {  // after initCells / an upload; afterwards every pass keeps them fresh
+            int rc = slab_exchange(g, c0->arena_off(c0->psi), top, c0->G, true);
+            if (rc) return rc;
+            for (mg_ctx *c : g->m) c->u_ghost_dirty = false;
         }
         return slab_twogrid(g, 1.0 / c0->size, c0->arena_off(c0->psi), c0->arena_off(c0->f), top);
     }
@@ -836,7 +911,7 @@ inline int mg_ctx::init(int dim_, int size_, int real_kind_, int smooth_, int de
     // arena layout: f, psi, psiOld, then per level R, V (below the top) and the ping-pong partner W
     auto up = [](size_t x) { return (x + mg::ARENA_ALIGN - 1) / mg::ARENA_ALIGN * mg::ARENA_ALIGN; };
     const int top = nlevels - 1;
-    size_t off = 0;
+    size_t off = mg::ARENA_HEADER;
     size_t o_f = off; off += up(Ntop * elem);
     size_t o_psi = off; off += up(Ntop * elem);
     size_t o_old = off; off += up(Ntop * elem);
@@ -884,6 +959,11 @@ inline int mg_ctx::init(int dim_, int size_, int real_kind_, int smooth_, int de
 inline void mg_ctx::release()
 {
     if (device >= 0) cudaSetDevice(device);
+    if (peer_ipc) {
+        if (peer_lo) cudaIpcCloseMemHandle(peer_lo);
+        if (peer_hi) cudaIpcCloseMemHandle(peer_hi);
+        peer_lo = peer_hi = nullptr;
+    }
     if (group && owns_group) {
         mg::SlabGroup *g = group;
         if (own_stream) cudaStreamSynchronize(stream);
@@ -1041,8 +1121,11 @@ static inline int mg_copy_impl(mg_ctx *c, int which, int level, void *host, size
             }
         }
     }
-    if (in && which == MG_BUF_F)
-        for (mg_ctx *m : (c->group ? c->group->m : std::vector<mg_ctx *>{c})) m->f_ghost_dirty = true;
+    if (in)
+        for (mg_ctx *m : (c->group ? c->group->m : std::vector<mg_ctx *>{c})) {
+            if (which == MG_BUF_F) m->f_ghost_dirty = true;
+            if (which == MG_BUF_PSI) m->u_ghost_dirty = true;
+        }
     MG_CK(c, cudaStreamSynchronize(c->stream));
     return MG_OK;
 }

@@ -165,6 +165,13 @@ template <typename R> struct Stream3DArgs {
     int nz_lo, nz_hi, zdom0, zdom1;
     int rz_off;       // RES: coarse local plane = ((p - nz_lo) >> 1) + rz_off
     int vz_off;       // PRO: coarse local plane = ((p - zdom0) >> 1) + vz_off
+    // Fused halo exchange (multi-GPU): the thread that writes one of this rank's G boundary
+    // planes also stores it into the neighbour's ghost planes, directly over NVLink (the peers'
+    // arenas are mapped with CUDA IPC and have the same layout, so the same element offset
+    // applies). peer_lo / peer_hi = the dst field in the lower / upper neighbour (or null);
+    // rpeer_lo / rpeer_hi = Rout there (RES, coarse level distributed). ghost = G.
+    R *peer_lo, *peer_hi, *rpeer_lo, *rpeer_hi;
+    int ghost;
 };
 
 template <typename R, typename A, int S, bool PRO, bool RES, int TX, int TY>
@@ -428,6 +435,18 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                     R *d = dst0 + sLL * (size_t)p;
                     if (st0) *(VT *)d = Vec<R>::pack(outv);
                     if (st1) *(VT *)(d + sL) = Vec<R>::pack(outv + VX);
+                    // boundary planes also land in the neighbours' ghost planes (peer stores)
+                    const int nown = a.nz_hi - a.nz_lo;
+                    if (a.peer_lo != nullptr && p - a.nz_lo < a.ghost) {       // -> lower rank's upper ghost
+                        R *pd = a.peer_lo + (dst0 - a.dst) + sLL * (size_t)(p + nown);
+                        if (st0) *(VT *)pd = Vec<R>::pack(outv);
+                        if (st1) *(VT *)(pd + sL) = Vec<R>::pack(outv + VX);
+                    }
+                    if (a.peer_hi != nullptr && a.nz_hi - p <= a.ghost) {      // -> upper rank's lower ghost
+                        R *pd = a.peer_hi + (dst0 - a.dst) + sLL * (size_t)(p - nown);
+                        if (st0) *(VT *)pd = Vec<R>::pack(outv);
+                        if (st1) *(VT *)(pd + sL) = Vec<R>::pack(outv + VX);
+                    }
                 }
             } else if ((ST || (p >= z0 && p < z1)) && st0 && st1) {
                 // restriction: children in the order i fastest, then j, then k (SURVEY 8(a'))
@@ -448,7 +467,11 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                         sacc = Ar<A>::add(sacc, (A)outv[2 * cidx + 1]);
                         sacc = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx]);
                         sacc = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx + 1]);
-                        a.Rout[cb + cidx] = (R)Ar<A>::mul((A).125, sacc);
+                        const R rv = (R)Ar<A>::mul((A).125, sacc);
+                        a.Rout[cb + cidx] = rv;
+                        const int qc = (p - a.nz_lo) >> 1, nc = (a.nz_hi - a.nz_lo) >> 1;   // coarse owned index / count
+                        if (a.rpeer_lo != nullptr && qc < a.ghost) a.rpeer_lo[cb + cidx + (size_t)L2 * L2 * (size_t)nc] = rv;
+                        if (a.rpeer_hi != nullptr && qc >= nc - a.ghost) a.rpeer_hi[cb + cidx - (size_t)L2 * L2 * (size_t)nc] = rv;
                     }
                 }
             }

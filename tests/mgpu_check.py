@@ -24,8 +24,8 @@ def main():
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     pkg = load_package()
     ok = True
-    for real in ("float", "double"):
-        s = pkg.create_distributed(size, real, dim=3)
+    for real, p2p in (("float", True), ("double", True), ("float", False)):
+        s = pkg.create_distributed(size, real, dim=3, p2p=p2p)
         errs = [s.step() for _ in range(3)]
         mine = torch.from_numpy(s.psi.download()).cuda()
         parts = [torch.empty_like(mine) for _ in range(world)]
@@ -38,7 +38,7 @@ def main():
             ref_errs = [one.step() for _ in range(3)]
             same = full.tobytes() == one.psi.download().tobytes()
             eok = all(abs(a - b) <= 1e-9 * abs(b) for a, b in zip(errs, ref_errs))
-            print(f"[mgpu_check] {world} GPUs, {size}^3 {real}: psi bit-identical to 1 GPU: {same}; "
+            print(f"[mgpu_check] {world} GPUs, {size}^3 {real}, {'fused peer-store' if p2p else 'NCCL send/recv'} halos: psi bit-identical to 1 GPU: {same}; "
                   f"err {errs} vs {ref_errs}: {eok}; slab info {s.slab_info()}", flush=True)
             ok = ok and same and eok
             one.close()

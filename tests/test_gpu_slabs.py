@@ -12,11 +12,16 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("size,P,real", [(128, 2, "float"), (128, 4, "float"), (256, 8, "float"),
                                          (128, 2, "double"), (128, 4, "float_acc64"), (256, 4, "float")])
-def test_local_slab_group_matches_single_solver(mgp, size, P, real):
+@pytest.mark.parametrize("p2p", [1, 0])
+def test_local_slab_group_matches_single_solver(mgp, size, P, real, p2p):
+    """p2p=1: the smoother kernel itself stores its boundary planes into the neighbour slab's ghost
+    planes (the fused NVLink exchange, here through same-device pointers); p2p=0: separate copies
+    (what ncclSend/ncclRecv do)."""
     one = mgp.MultigridCUDA(size, real, dim=3, out=False)
     one.set_tuning(tb=4)
     one.set_option("stream_min_L", 64)
     grp = mgp.MultigridCUDA(size, real, dim=3, out=False, local_slabs=P)
+    grp.set_option("slab_p2p", p2p)
     info = grp.slab_info()
     assert info["nranks"] == P and info["own_planes"] == size // P and info["ghost"] == 4
     assert_bits_equal(grp.f.download(), one.f.download(), "f after initCells")
@@ -29,7 +34,7 @@ def test_local_slab_group_matches_single_solver(mgp, size, P, real):
     for L in (32, 16, 1):
         assert_bits_equal(grp.Vs[L].download(), one.Vs[L].download(), f"Vs[{L}]")
         assert_bits_equal(grp.Rs[L].download(), one.Rs[L].download(), f"Rs[{L}]")
-    assert grp.slab_info()["exchanges"] > 0
+    assert (grp.slab_info()["exchanges"] > 10) == (p2p == 0)
     one.close(); grp.close()
 
 
