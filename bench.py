@@ -237,8 +237,8 @@ def run_ours(args):
     unit_scale = (float(gsize) / args.size) ** args.dim if world > 1 else 1.0
     if world == 1:
         s.set_tuning(tb=args.tb, small_L=args.small_L, use_graph=0 if args.no_graph else 1)
-    elif args.tb >= 0:
-        s.set_tuning(tb=args.tb)
+    else:
+        s.set_tuning(tb=args.tb, use_graph=0 if args.no_graph else 1)
     for kv in args.opt:
         k, v = kv.split("=")
         s.set_option(k, int(v))

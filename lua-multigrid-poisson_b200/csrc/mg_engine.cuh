@@ -141,7 +141,7 @@ struct mg_ctx {
     // fused halo exchange over peer memory: the neighbours' arenas (same layout as ours), mapped
     // with CUDA IPC (other process) or simply their pointers (same process). p2p = use them.
     char *peer_lo = nullptr, *peer_hi = nullptr;
-    bool peer_ipc = false, p2p = false;
+    bool peer_ipc = false, p2p = false, slab_graph_opt = false;
     size_t Ntop = 0;                    // elements allocated for a top-level field (incl. ghosts)
 
     int planes(int lv) const { return dist[lv] ? nzl[lv] + 2 * G : (dim == 3 ? (1 << lv) : 1); }
@@ -890,7 +890,6 @@ inline int mg_ctx::init(int dim_, int size_, int real_kind_, int smooth_, int de
         if (!dist[nlevels - 1]) return fail(MG_EINVAL, "grid too small to be cut into slabs (need size >= 64 and size/nranks >= 8)");
         stream_min_L = 64;
         tb = 4;
-        use_graph = 0;
     }
     N = (size_t)size * size * (dim == 3 ? (size_t)size : 1);
     Ntop = level_elems(nlevels - 1);
@@ -1155,14 +1154,20 @@ inline int mg_ctx::vcycle()
         if (rc) return rc;
         return eng->twogrid_refseq(this, h, psi, f, top);
     }
-    if (group) return eng->slab_vcycle(group);
-    if (!use_graph) return eng->twogrid_fused(this, h, psi, f, top);
+    // Slabs: the first cycle after initCells / an upload refreshes ghosts with explicit exchanges and
+    // runs eagerly; afterwards (fused halo exchange, one process per GPU) the whole cycle --
+    // smoother passes, handshake kernels, the all-gather of the replicated level -- is one graph.
+    // (Off by default: "slab_graph" option. With libnccl 2.28 the captured cycle dead-locked on a
+    // 2-GPU box -- the all-gather inside the capture is the suspect -- so slabs launch eagerly.)
+    const bool slab_graph = group && group->nccl && p2p && use_graph && slab_graph_opt && !f_ghost_dirty && !u_ghost_dirty;
+    if (group && !slab_graph) return eng->slab_vcycle(group);
+    if (!group && !use_graph) return eng->twogrid_fused(this, h, psi, f, top);
     if (!gexec) {
         cudaStream_t saved = stream;
         MG_CK(this, cudaStreamSynchronize(saved));
         MG_CK(this, cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
         stream = cap_stream; capturing = true;
-        int rc = eng->twogrid_fused(this, h, psi, f, top);
+        int rc = group ? eng->slab_vcycle(group) : eng->twogrid_fused(this, h, psi, f, top);
         stream = saved; capturing = false;
         cudaError_t e = cudaStreamEndCapture(cap_stream, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); graph = nullptr; return rc; }
