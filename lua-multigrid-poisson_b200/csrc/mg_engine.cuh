@@ -5,6 +5,7 @@
 
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -119,9 +120,9 @@ struct mg_ctx {
     // ---- streams / graph
     cudaStream_t own_stream = nullptr, stream = nullptr, cap_stream = nullptr;
     bool borrowed_stream = false, capturing = false;
-    cudaGraph_t graph = nullptr;
-    cudaGraphExec_t gexec = nullptr;
-    size_t graph_nodes = 0;
+    cudaGraph_t graph = nullptr, rep_graph = nullptr;       // rep_*: replicated coarse sub-cycle of a slab
+    cudaGraphExec_t gexec = nullptr, rep_gexec = nullptr;
+    size_t graph_nodes = 0, rep_nodes = 0;
     uint64_t launches = 0;
 
     bool prof_on = false;
@@ -418,7 +419,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         if (ncta > work / 2) ncta = work / 2 > 0 ? work / 2 : 1;
         dim3 grid((unsigned)ncta, 1, 1);
         Stream3DArgs<R> a{dst, Vp, Rout, L, 0, c->stream_flags, nz_lo, nz_hi, zdom0, zdom0 + L, rz_off, vz_off,
-                          nullptr, nullptr, nullptr, nullptr, c->G};
+                          nullptr, nullptr, nullptr, nullptr, c->G, nullptr, nullptr, nullptr};
         if (c->dist[lv] && c->p2p) {  // fused halo exchange: same offsets inside the neighbours' arenas
             const size_t doff = c->arena_off(dst);
             if (c->peer_lo) a.peer_lo = (R *)(c->peer_lo + doff);
@@ -427,6 +428,11 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
                 const size_t roff = c->arena_off(Rout);
                 if (c->peer_lo) a.rpeer_lo = (R *)(c->peer_lo + roff);
                 if (c->peer_hi) a.rpeer_hi = (R *)(c->peer_hi + roff);
+            }
+            if (c->group && c->group->nccl) {  // other processes: handshake inside the kernel
+                a.hs = (unsigned long long *)c->arena;
+                a.hs_lo = (unsigned long long *)c->peer_lo;
+                a.hs_hi = (unsigned long long *)c->peer_hi;
             }
         }
         c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : (RES ? MG_K_SWEEP_RESTRICT : MG_K_SWEEP), L, S);
@@ -484,18 +490,13 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
     int slab_wait(SlabGroup *g)
     {
         mg_ctx *c = g->m[0];
-        if (!c->p2p || !g->nccl) return MG_OK;
-        k_slab_wait<<<1, 1, 0, c->stream>>>((const unsigned long long *)c->arena, c->peer_lo != nullptr, c->peer_hi != nullptr);
-        MG_LAUNCH_CHECK(c);
+        (void)c;   // the handshake lives inside k_stream3d (Stream3DArgs::hs); nothing to launch
         return MG_OK;
     }
     int slab_signal(SlabGroup *g)
     {
         mg_ctx *c = g->m[0];
-        if (!c->p2p || !g->nccl) return MG_OK;
-        k_slab_signal<<<1, 1, 0, c->stream>>>((unsigned long long *)c->arena, (unsigned long long *)c->peer_lo,
-                                              (unsigned long long *)c->peer_hi);
-        MG_LAUNCH_CHECK(c);
+        (void)c;
         return MG_OK;
     }
     int slab_exchange(SlabGroup *g, size_t off, int lv, int depth, bool force = false)
@@ -559,6 +560,28 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         mg_ctx *c0 = g->m[0];
         int rc;
         if (!c0->dist[lv]) {  // replicated: every rank runs the ordinary single-GPU path
+            if (g->nccl && c0->use_graph && !c0->capturing && !c0->prof_on) {
+                // one process per GPU: replay the whole coarse sub-cycle (dozens of small launches,
+                // no communication inside) from its own CUDA graph
+                mg_ctx *c = c0;
+                if (!c->rep_gexec) {
+                    cudaStream_t saved = c->stream;
+                    MG_CK(c, cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
+                    c->stream = c->cap_stream; c->capturing = true;
+                    rc = twogrid_fused(c, h, at(c, u_off), at(c, f_off), lv);
+                    c->stream = saved; c->capturing = false;
+                    cudaError_t e = cudaStreamEndCapture(c->cap_stream, &c->rep_graph);
+                    if (rc) return rc;
+                    if (e != cudaSuccess) return c->fail_cuda(e, "cudaStreamEndCapture (replicated levels)");
+                    MG_CK(c, cudaGraphInstantiate(&c->rep_gexec, c->rep_graph, 0));
+                    size_t nn = 0;
+                    MG_CK(c, cudaGraphGetNodes(c->rep_graph, nullptr, &nn));
+                    c->rep_nodes = nn;
+                }
+                MG_CK(c, cudaGraphLaunch(c->rep_gexec, c->stream));
+                c->launches += c->rep_nodes;
+                return MG_OK;
+            }
             for (mg_ctx *c : g->m)
                 if ((rc = twogrid_fused(c, h, at(c, u_off), at(c, f_off), lv))) return rc;
             return MG_OK;
@@ -883,9 +906,13 @@ inline int mg_ctx::init(int dim_, int size_, int real_kind_, int smooth_, int de
         if (dim != 3) return fail(MG_EUNSUPPORTED, "slab decomposition is 3-D only");
         if (nranks > 8 || (nranks & (nranks - 1))) return fail(MG_EINVAL, "nranks must be 2, 4 or 8");
         G = 4;
+        // a level is cut across the ranks while every rank keeps at least this many planes
+        // (>= 8 = two ghost depths); thinner levels are replicated. MGPOISSON_SLAB_MIN_PLANES tunes it.
+        int min_planes = 8;
+        if (const char *e = getenv("MGPOISSON_SLAB_MIN_PLANES")) min_planes = atoi(e) < 8 ? 8 : atoi(e);
         for (int lv = 0; lv < nlevels; ++lv) {
             const int L = 1 << lv;
-            if (L >= 64 && L / nranks >= 8) { dist[lv] = true; nzl[lv] = L / nranks; }
+            if (L >= 64 && L / nranks >= min_planes) { dist[lv] = true; nzl[lv] = L / nranks; }
         }
         if (!dist[nlevels - 1]) return fail(MG_EINVAL, "grid too small to be cut into slabs (need size >= 64 and size/nranks >= 8)");
         stream_min_L = 64;
@@ -1141,7 +1168,9 @@ inline void mg_ctx::drop_graph()
 {
     if (gexec) cudaGraphExecDestroy(gexec);
     if (graph) cudaGraphDestroy(graph);
-    gexec = nullptr; graph = nullptr; graph_nodes = 0;
+    if (rep_gexec) cudaGraphExecDestroy(rep_gexec);
+    if (rep_graph) cudaGraphDestroy(rep_graph);
+    gexec = rep_gexec = nullptr; graph = rep_graph = nullptr; graph_nodes = rep_nodes = 0;
 }
 
 // twoGrid(1/size, psi, f, size) (cpu-raw.lua:247)

@@ -172,7 +172,23 @@ template <typename R> struct Stream3DArgs {
     // rpeer_lo / rpeer_hi = Rout there (RES, coarse level distributed). ghost = G.
     R *peer_lo, *peer_hi, *rpeer_lo, *rpeer_hi;
     int ghost;
+    // Handshake of the fused exchange, folded into the kernel (one process per GPU only):
+    // hs = this rank's arena header {[0] passes completed, [16] / [32] passes the lower / upper
+    // neighbour has published, [48] CTAs of the current pass that are done}; hs_lo / hs_hi = the
+    // neighbours' headers (null at the ends of the chain, and everywhere when hs is null).
+    unsigned long long *hs, *hs_lo, *hs_hi;
 };
+
+__device__ __forceinline__ unsigned long long s3_ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void s3_st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 
 template <typename R, typename A, int S, bool PRO, bool RES, int TX, int TY>
 __global__ void __launch_bounds__((Stream3DCfg<R, S, RES, TX, TY>::NTHREADS), 1)
@@ -201,6 +217,17 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     const int L = a.L;
     const int zdom0 = a.zdom0, zdom1 = a.zdom1;
     bool first_chunk = true;
+
+    // Before touching ghost planes (ours, by TMA; the neighbours', by peer stores): both
+    // neighbours must have finished as many passes as we have. Every CTA checks for itself.
+    if (a.hs != nullptr) {
+        if (threadIdx.x == 0) {
+            const unsigned long long n = s3_ld_acquire_sys(a.hs);
+            if (a.hs_lo != nullptr) while (s3_ld_acquire_sys(a.hs + 16) < n) { }
+            if (a.hs_hi != nullptr) while (s3_ld_acquire_sys(a.hs + 32) < n) { }
+        }
+        __syncthreads();
+    }
 
     // One chunk = tile (x0, y0) streamed through the owned planes [z0, z1). A CTA may process
     // several chunks (balanced persistent partition, see the end of the kernel).
@@ -532,6 +559,23 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
             const long long n = min(npair - zp, hi - lo);
             run_chunk((int)(tile % ntx) * TX, (int)(tile / ntx) * TY, a.nz_lo + 2 * (int)zp, a.nz_lo + 2 * (int)(zp + n));
             lo += n;
+        }
+    }
+
+    // The last CTA of the pass publishes "pass n+1 done" to both neighbours: all our stores,
+    // local and into their ghost planes, are ordered before it.
+    if (a.hs != nullptr) {
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence_system();
+            const unsigned int done = atomicAdd(reinterpret_cast<unsigned int *>(a.hs + 48), 1u);
+            if (done == gridDim.x - 1) {
+                *reinterpret_cast<volatile unsigned int *>(a.hs + 48) = 0u;
+                const unsigned long long n = s3_ld_acquire_sys(a.hs) + 1;
+                s3_st_release_sys(a.hs, n);
+                if (a.hs_lo != nullptr) s3_st_release_sys(a.hs_lo + 32, n);   // we are its upper neighbour
+                if (a.hs_hi != nullptr) s3_st_release_sys(a.hs_hi + 16, n);   // and its lower neighbour
+            }
         }
     }
 }
