@@ -162,7 +162,7 @@ class DeviceBuffer:
     @property
     def shape(self):
         o = self.owner
-        if o.slab_n > 1 and self.L >= 64 and self.L // o.slab_n >= max(8, int(os.environ.get("MGPOISSON_SLAB_MIN_PLANES", "8"))):
+        if o.slab_n > 1 and self.L >= 64 and self.L // o.slab_n >= max(8, int(os.environ.get("MGPOISSON_SLAB_MIN_PLANES", "32"))):
             return (self.L // o.slab_n,) + (self.L,) * (o.dim - 1)
         return (self.L,) * o.dim
 
@@ -494,7 +494,7 @@ def slab_partition(size, nranks):
     widths are cut across the ranks, planes per rank, ghost depth, and the replicated levels."""
     levels, L = [], size
     while L >= 1:
-        d = nranks > 1 and L >= 64 and L // nranks >= max(8, int(os.environ.get("MGPOISSON_SLAB_MIN_PLANES", "8")))
+        d = nranks > 1 and L >= 64 and L // nranks >= max(8, int(os.environ.get("MGPOISSON_SLAB_MIN_PLANES", "32")))
         levels.append(dict(L=L, distributed=d, planes_per_rank=L // nranks if d else L, ghost=4 if d else 0))
         L //= 2
     return levels

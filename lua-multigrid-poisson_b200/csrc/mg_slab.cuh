@@ -2,7 +2,7 @@
 //
 // The reference has no multi-device path (gpu.lua:27-30 picks one device); this is new work
 // behind the same V-cycle semantics. The grid is cut along z (the slowest axis): rank r owns
-// planes [r*L/P, (r+1)*L/P) of every DISTRIBUTED level (L >= 64 and L/P >= 8). Distributed
+// planes [r*L/P, (r+1)*L/P) of every DISTRIBUTED level (L >= 64 and L/P >= 32 by default). Distributed
 // fields carry G = 4 ghost planes on each side; before a smoother pass with NST pipeline stages
 // the source field's ghosts are refreshed to depth NST from the two neighbours. Restriction and
 // prolongation are communication-free (children 2K, 2K+1 live on the same rank); only ghosts of

@@ -12,11 +12,14 @@ pytestmark = pytest.mark.gpu
 
 @pytest.mark.parametrize("size,P,real", [(128, 2, "float"), (128, 4, "float"), (256, 8, "float"),
                                          (128, 2, "double"), (128, 4, "float_acc64"), (256, 4, "float")])
-@pytest.mark.parametrize("p2p", [1, 0])
-def test_local_slab_group_matches_single_solver(mgp, size, P, real, p2p):
+@pytest.mark.parametrize("p2p,min_planes", [(1, 8), (0, 8), (1, 32)])
+def test_local_slab_group_matches_single_solver(mgp, monkeypatch, size, P, real, p2p, min_planes):
     """p2p=1: the smoother kernel itself stores its boundary planes into the neighbour slab's ghost
     planes (the fused NVLink exchange, here through same-device pointers); p2p=0: separate copies
     (what ncclSend/ncclRecv do)."""
+    monkeypatch.setenv("MGPOISSON_SLAB_MIN_PLANES", str(min_planes))   # replication threshold (default 32)
+    if size // P < min_planes:
+        pytest.skip("top level would not be distributed")
     one = mgp.MultigridCUDA(size, real, dim=3, out=False)
     one.set_tuning(tb=4)
     one.set_option("stream_min_L", 64)
@@ -34,11 +37,12 @@ def test_local_slab_group_matches_single_solver(mgp, size, P, real, p2p):
     for L in (32, 16, 1):
         assert_bits_equal(grp.Vs[L].download(), one.Vs[L].download(), f"Vs[{L}]")
         assert_bits_equal(grp.Rs[L].download(), one.Rs[L].download(), f"Rs[{L}]")
-    assert (grp.slab_info()["exchanges"] > 10) == (p2p == 0)
+    assert (grp.slab_info()["exchanges"] > 6) == (p2p == 0)
     one.close(); grp.close()
 
 
-def test_local_slab_group_random_rhs_vs_oracle(mgp, orc):
+def test_local_slab_group_random_rhs_vs_oracle(mgp, orc, monkeypatch):
+    monkeypatch.setenv("MGPOISSON_SLAB_MIN_PLANES", "8")
     size, P = 128, 4
     rng = np.random.default_rng(1234)
     grp = mgp.MultigridCUDA(size, "float", dim=3, out=False, local_slabs=P)
@@ -54,7 +58,11 @@ def test_local_slab_group_random_rhs_vs_oracle(mgp, orc):
     grp.close()
 
 
-def test_slab_partition_description(mgp):
+def test_slab_partition_description(mgp, monkeypatch):
+    monkeypatch.delenv("MGPOISSON_SLAB_MIN_PLANES", raising=False)
+    lv = mgp.slab_partition(1024, 8)            # default: a level stays cut while every rank keeps >= 32 planes
+    assert [x["L"] for x in lv if x["distributed"]] == [1024, 512, 256]
+    monkeypatch.setenv("MGPOISSON_SLAB_MIN_PLANES", "8")
     lv = mgp.slab_partition(1024, 8)
     assert [x["L"] for x in lv if x["distributed"]] == [1024, 512, 256, 128, 64]
     assert lv[0]["planes_per_rank"] == 128 and lv[4]["planes_per_rank"] == 8

@@ -134,7 +134,13 @@ def free_port():
         return s.getsockname()[1]
 
 
-def test_schedule_description(mgp):
+def test_schedule_description(mgp, monkeypatch):
+    monkeypatch.delenv("MGPOISSON_SLAB_MIN_PLANES", raising=False)
+    ops = mgp.slab_schedule(1024, 8)            # default threshold: 32 planes per rank
+    assert sorted({L for op, L, _ in ops if op == "pass"}, reverse=True) == [1024, 512, 256]
+    assert ("allgather_R", 128, None) in ops and ("replicated_vcycle", 128, None) in ops
+    assert sum(1 for op, _, _ in ops if op.startswith("exchange")) == 17
+    monkeypatch.setenv("MGPOISSON_SLAB_MIN_PLANES", "8")
     ops = mgp.slab_schedule(1024, 8)
     lv = [L for op, L, _ in ops if op == "pass"]
     assert sorted(set(lv), reverse=True) == [1024, 512, 256, 128, 64]
@@ -150,7 +156,8 @@ def test_schedule_description(mgp):
 
 
 @pytest.mark.timeout(600)
-def test_two_rank_gloo_slab_vcycle_matches_oracle(tmp_path, orc):
+def test_two_rank_gloo_slab_vcycle_matches_oracle(tmp_path, orc, monkeypatch):
+    monkeypatch.setenv("MGPOISSON_SLAB_MIN_PLANES", "8")   # two distributed levels (128, 64) below a replicated 32
     size, world, cycles = 128, 2, 2
     out = str(tmp_path / "psi.npy")
     mp.spawn(worker, args=(world, free_port(), size, cycles, out), nprocs=world, join=True)
