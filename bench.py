@@ -373,8 +373,9 @@ def run_ours(args):
             si = s.slab_info()
             line["config"].update({
                 "workload": f"{args.dim}D {gsize}^{args.dim} {dtype_name(args.real)} Poisson V-cycle cut into {world} z-slabs "
-                            f"({si['own_planes']} planes + {si['ghost']} ghost planes per side per GPU), NCCL send/recv halo "
-                            f"exchange before every smoother pass, levels below 64 replicated",
+                            f"({si['own_planes']} planes + {si['ghost']} ghost planes per side per GPU); halo planes are stored "
+                            f"into the neighbour's ghost planes by the smoother kernel itself over NVLink peer memory "
+                            f"(CUDA IPC), handshake inside the kernel; levels with < 32 planes per GPU replicated (NCCL all-gather)",
                 "baseline_config": "configs[3] (3D 1024^3 fp32 slab-decomposed across 2/4/8 B200)",
                 "grid": [gsize] * args.dim, "parallelism": f"z-slabs x{world}",
                 "unit": f"value counts V-cycles of the N=1 workload ({args.size}^{args.dim}); one {gsize}^{args.dim} V-cycle = {unit_scale:g} units",
