@@ -117,6 +117,8 @@ int mg_set_option(mg_ctx *ctx, const char *name, int value)
             m->u_ghost_dirty = m->f_ghost_dirty = true;
         }
     }
+    else if (n == "tile_y") ctx->tile_y_opt = value;
+    else if (n == "lockstep") ctx->lockstep_opt = value;
     else if (n == "slab_graph") ctx->slab_graph_opt = value != 0;
     else if (n == "tma_promo") { ctx->tma_promo = value; ctx->tmaps.clear(); }
     else if (n == "tb2") { if (value < 0 || value > 7) return ctx->fail(MG_EINVAL, "tb2 must be 0..7"); ctx->tb2 = value; }

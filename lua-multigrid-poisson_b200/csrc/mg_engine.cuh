@@ -93,6 +93,8 @@ struct mg_ctx {
     int ty_override = 0;     // 2-D: rows per warp work item (0 = cost model)
     int stream_min_L = 128;  // smallest level width handled by the streaming (TMA) smoother
     int num_sms = 148;       // SM count of the device (queried at init)
+    int tile_y_opt = 0;      // 0 = automatic, else force the float tile's y extent (24 or 22)
+    int lockstep_opt = 0;    // lock-step column mode of the streaming smoother (off: measured slower)
     int tma_promo = 3;       // L2 promotion of the TMA descriptors: 0 none, 1 64 B, 2 128 B, 3 256 B
     int stream_flags = 0;    // debug switches of the streaming smoother (see Stream3DArgs::flags)
     int tz_override = 0;     // planes per CTA of the streaming smoother (0 = cost model)
@@ -355,19 +357,49 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
     // n sweeps starting from `cur` (ping-pong with `oth`), the first optionally reading
     // cur + prolong(Vp), followed optionally by Rout = restrict(f - A cur).
     // ---- streaming (TMA, temporally blocked) smoother passes, 3-D only
+    // the y extent of the float tile is chosen per launch (see pick_tile_y)
+    static constexpr int kTileX = sizeof(R) == 4 ? 88 : 32;
+    static constexpr int kTileYA = sizeof(R) == 4 ? 24 : 32, kTileYB = kTileYA;   // (88 x 22 tried: see below)
+    // Lock-step mode: when the tile columns of a level fit the resident CTAs almost exactly
+    // (>= 90 %), give every CTA one whole column: all columns then march through z together and
+    // the halo rows neighbouring tiles share are served from L2 instead of HBM. At 512^2 planes a
+    // tile of 88 x 22 gives 6 x 24 = 144 columns for 148 SMs; 88 x 24 gives 132 (89 %).
+    // MEASURED (round 1, 512^3): lock-step 88 x 22 = 242 V-cycles/s, balanced 88 x 24 = 260: the
+    // passes are not HBM-bound, so the balanced partition stays the default ("lockstep" = 0).
+    static int pick_tile_y(mg_ctx *c, int L, bool *lockstep)
+    {
+        *lockstep = false;
+        if (c->tile_y_opt == kTileYA || c->tile_y_opt == kTileYB) {
+            const long t = (long)((L + kTileX - 1) / kTileX) * ((L + c->tile_y_opt - 1) / c->tile_y_opt);
+            *lockstep = c->lockstep_opt != 0 && t <= c->num_sms;
+            return c->tile_y_opt;
+        }
+        if (c->lockstep_opt == 0) return kTileYA;
+        for (int ty : {kTileYA, kTileYB}) {
+            const long t = (long)((L + kTileX - 1) / kTileX) * ((L + ty - 1) / ty);
+            if (t <= c->num_sms && t * 10 >= (long)c->num_sms * 9) { *lockstep = true; return ty; }
+        }
+        return kTileYA;
+    }
     template <int S, bool PRO, bool RES>
     int launch_stream3d(mg_ctx *c, int lv, R *dst, const R *src, const R *f, const R *Vp, R *Rout, const Coef<A> &cf)
     {
+        bool lockstep = false;
+        const int ty = pick_tile_y(c, 1 << lv, &lockstep);
+        if (ty == kTileYB && kTileYB != kTileYA)
+            return launch_stream3d_t<S, PRO, RES, kTileYB>(c, lv, dst, src, f, Vp, Rout, cf, lockstep);
+        return launch_stream3d_t<S, PRO, RES, kTileYA>(c, lv, dst, src, f, Vp, Rout, cf, lockstep);
+    }
+    template <int S, bool PRO, bool RES, int TY>
+    int launch_stream3d_t(mg_ctx *c, int lv, R *dst, const R *src, const R *f, const R *Vp, R *Rout, const Coef<A> &cf,
+                          bool lockstep)
+    {
         const int L = 1 << lv;
-        // In-plane tile. 4-byte reals: 88 x 24 (+ halo = 96 x 32): 24 vectors per row and a 384-byte
-        // row pitch, so every quarter-warp of a 128-bit shared-memory access stays inside one row
-        // and is bank-conflict free; tiles need not divide the grid (balanced partition + masks).
+        // In-plane tile. 4-byte reals: 88 x 24 or 88 x 22 (+ halo = 96 wide): 24 vectors per row and a
+        // 384-byte row pitch, so every quarter-warp of a 128-bit shared-memory access stays inside
+        // one row and is bank-conflict free; tiles need not divide the grid (masks + partition).
         // 8-byte reals: 32 x 32 (shared-memory budget).
-#ifndef MG_TILE_X
-#define MG_TILE_X 88
-#define MG_TILE_Y 24
-#endif
-        constexpr int TX = sizeof(R) == 4 ? MG_TILE_X : 32, TY = sizeof(R) == 4 ? MG_TILE_Y : 32;
+        constexpr int TX = kTileX;
         typedef Stream3DCfg<R, S, RES, TX, TY> C;
         const CUtensorMap *map = nullptr, *fmap = nullptr;
         const int nplanes = c->planes(lv);
@@ -396,6 +428,8 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         long ncta;
         if (c->tz_override > 0) {
             ncta = (work + c->tz_override - 1) / c->tz_override;
+        } else if (lockstep) {
+            ncta = tiles;   // one whole column per CTA (the balanced partition degenerates to this)
         } else if (S <= 2) {
             // Shallow passes are HBM-bound: keep whole tile columns marching through z in lock
             // step, so that the halo rows neighbouring tiles share are still in L2 when the
