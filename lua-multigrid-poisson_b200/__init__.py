@@ -114,6 +114,8 @@ def lib():
         "mg_frob_err": (i, [vp, pd]),
         "mg_smooth_residual_restrict": (i, [vp, i, vp, vp, d, i, vp]),
         "mg_prolong_add_smooth": (i, [vp, i, vp, vp, d, i, vp]),
+        "mg_cg": (i, [vp, i, d, pd, pd, pi]),
+        "mg_linf_norm": (i, [vp, i, i, pd]),
         "mg_trace_enable": (i, [vp, i]),
         "mg_trace_clear": (i, [vp]),
         "mg_trace_count": (sz, [vp]),
@@ -350,6 +352,20 @@ class MultigridCUDA:
         e = C.c_double()
         self._ck(lib().mg_frob_err(self._h, C.byref(e)))
         return e.value
+
+    # -------------------------------------------------------------- Krylov comparator
+    def conjgrad(self, max_iter=1000, epsilon=1e-20):
+        """test/converge-multigrid-vs-krylov.lua:38-69: CG on the same operator, b = f, x = psi as found.
+        Returns (errs, linf_of_x) per iteration."""
+        errs, linf = (C.c_double * max(max_iter, 1))(), (C.c_double * max(max_iter, 1))()
+        n = C.c_int()
+        self._ck(lib().mg_cg(self._h, int(max_iter), float(epsilon), errs, linf, C.byref(n)))
+        return [errs[k] for k in range(n.value)], [linf[k] for k in range(n.value)]
+
+    def linf_norm(self, which=BUF_PSI, L=None) -> float:
+        v = C.c_double()
+        self._ck(lib().mg_linf_norm(self._h, which, L or self.size, C.byref(v)))
+        return v.value
 
     # -------------------------------------------------------------- per-operator (device ptrs)
     def jacobi(self, L, dest, u, f, h):

@@ -374,6 +374,25 @@ int mg_prolong_add_smooth(mg_ctx *ctx, int L, void *u, const void *f, double h, 
     return ctx->sync();
 }
 
+// ------------------------------------------------------------------ Krylov comparator
+int mg_cg(mg_ctx *ctx, int max_iter, double epsilon, double *err_hist, double *linf_hist, int *n_done)
+{
+    CTX_OR_FAIL(ctx);
+    if (max_iter < 0) return ctx->fail(MG_EINVAL, "mg_cg: max_iter < 0");
+    return ctx->eng->cg(ctx, max_iter, epsilon, err_hist, linf_hist, n_done);
+}
+
+int mg_linf_norm(mg_ctx *ctx, int which, int level, double *out)
+{
+    CTX_OR_FAIL(ctx);
+    if (!out) return MG_EINVAL;
+    if (ctx->group) return ctx->fail(MG_EUNSUPPORTED, "mg_linf_norm: single-GPU only");
+    size_t cap = 0;
+    void *d = ctx->buffer(which, level, &cap);
+    if (!d) return ctx->fail(MG_EINVAL, "mg_linf_norm: no such buffer");
+    return ctx->eng->linf_norm(ctx, d, cap / ctx->elem, out);
+}
+
 // ------------------------------------------------------------------ trace
 int mg_trace_enable(mg_ctx *ctx, int on)
 {

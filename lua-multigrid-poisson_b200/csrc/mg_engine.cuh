@@ -14,6 +14,7 @@
 
 #include "../../include/mgpoisson.h"
 #include "mg_fused_simple.cuh"
+#include "mg_krylov.cuh"
 #include "mg_math.cuh"
 #include "mg_ops_ref.cuh"
 #include "mg_slab.cuh"
@@ -25,37 +26,8 @@ namespace mg {
 
 constexpr int MAX_LEVELS = 24;
 constexpr size_t ARENA_ALIGN = 1024;
-constexpr size_t ARENA_HEADER = 1024;   // pass counter + the two neighbour flags of the slab handshake
-
-// Handshake of the fused halo exchange (one process per GPU): words 0 / 16 / 32 of the arena are
-// this rank's pass counter and the counters its lower / upper neighbour last published.
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-// before pass n+1: both neighbours must have finished their pass n (their stores into our ghost
-// planes are complete, and they no longer read the ghost planes we are about to overwrite)
-__global__ void k_slab_wait(const unsigned long long *hdr, int has_lo, int has_hi)
-{
-    const unsigned long long n = hdr[0];
-    if (has_lo) while (ld_acquire_sys(hdr + 16) < n) { }
-    if (has_hi) while (ld_acquire_sys(hdr + 32) < n) { }
-}
-// after pass n+1: publish n+1 to both neighbours (the kernel boundary ordered our peer stores)
-__global__ void k_slab_signal(unsigned long long *hdr, unsigned long long *lo_hdr, unsigned long long *hi_hdr)
-{
-    const unsigned long long n = hdr[0] + 1;
-    hdr[0] = n;
-    __threadfence_system();
-    if (lo_hdr) st_release_sys(lo_hdr + 32, n);   // we are the lower neighbour's UPPER neighbour
-    if (hi_hdr) st_release_sys(hi_hdr + 16, n);   // and the upper neighbour's LOWER neighbour
-}
+constexpr size_t ARENA_HEADER = 1024;   // slab handshake words (Stream3DArgs::hs): [0] passes done,
+                                        // [16]/[32] passes published by the lower/upper neighbour, [48] CTAs done
 
 struct TraceRec {
     char name;
@@ -117,6 +89,7 @@ struct mg_ctx {
 
     // ---- reductions
     double *d_partial = nullptr, *d_scalar = nullptr, *h_scalar = nullptr;
+    void *cg_tmp = nullptr;   // scratch of mg_cg (one field + reduction space), allocated on first use
     int npartial = 0;
 
     // ---- streams / graph
@@ -224,6 +197,8 @@ struct Engine {
     virtual int frob_err(mg_ctx *c, double *err, bool materialise) = 0;
     virtual int residual_norm(mg_ctx *c, double *rms) = 0;
     virtual int slab_vcycle(SlabGroup *g) = 0;
+    virtual int cg(mg_ctx *c, int max_iter, double epsilon, double *err_hist, double *linf_hist, int *n_done) = 0;
+    virtual int linf_norm(mg_ctx *c, const void *field, size_t n, double *out) = 0;
     virtual int frob_partial_sum(mg_ctx *c, double *sum) = 0;
 };
 
@@ -452,7 +427,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         if (ncta < 1) ncta = 1;
         if (ncta > work / 2) ncta = work / 2 > 0 ? work / 2 : 1;
         dim3 grid((unsigned)ncta, 1, 1);
-        Stream3DArgs<R> a{dst, Vp, Rout, L, 0, c->stream_flags, nz_lo, nz_hi, zdom0, zdom0 + L, rz_off, vz_off,
+        Stream3DArgs<R> a{dst, Vp, Rout, L, c->stream_flags, nz_lo, nz_hi, zdom0, zdom0 + L, rz_off, vz_off,
                           nullptr, nullptr, nullptr, nullptr, c->G, nullptr, nullptr, nullptr};
         if (c->dist[lv] && c->p2p) {  // fused halo exchange: same offsets inside the neighbours' arenas
             const size_t doff = c->arena_off(dst);
@@ -519,20 +494,6 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
 
     // ---- slab V-cycle (mg_slab.cuh): the same schedule on every rank, halo planes in between
     static char *at(mg_ctx *c, size_t off) { return (char *)c->arena + off; }
-    // handshake around a pass of the fused-exchange mode (only needed across processes; slabs of
-    // one process share a stream, which already orders them)
-    int slab_wait(SlabGroup *g)
-    {
-        mg_ctx *c = g->m[0];
-        (void)c;   // the handshake lives inside k_stream3d (Stream3DArgs::hs); nothing to launch
-        return MG_OK;
-    }
-    int slab_signal(SlabGroup *g)
-    {
-        mg_ctx *c = g->m[0];
-        (void)c;
-        return MG_OK;
-    }
     int slab_exchange(SlabGroup *g, size_t off, int lv, int depth, bool force = false)
     {
         mg_ctx *c0 = g->m[0];
@@ -631,12 +592,10 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             for (int i = 0; i < np; ++i) {
                 const bool res = i == np - 1;
                 if ((rc = slab_exchange(g, cur, lv, plan[i] + (res ? 1 : 0)))) return rc;
-                if ((rc = slab_wait(g))) return rc;
                 for (mg_ctx *c : g->m)
                     if ((rc = stream3d_pass(c, lv, plan[i], false, res, (R *)at(c, oth), (const R *)at(c, cur),
                                             (const R *)at(c, f_off), nullptr, res ? (R *)at(c, Rc_off) : nullptr, cf)))
                         return rc;
-                if ((rc = slab_signal(g))) return rc;
                 size_t t = cur; cur = oth; oth = t;
             }
             // the restricted residual is the next level's right-hand side
@@ -649,12 +608,10 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             np = plan_passes(c0->smooth, c0->tb, false, plan);
             for (int i = 0; i < np; ++i) {
                 if ((rc = slab_exchange(g, cur, lv, plan[i]))) return rc;
-                if ((rc = slab_wait(g))) return rc;
                 for (mg_ctx *c : g->m)
                     if ((rc = stream3d_pass(c, lv, plan[i], i == 0, false, (R *)at(c, oth), (const R *)at(c, cur),
                                             (const R *)at(c, f_off), i == 0 ? (const R *)at(c, Vc_off) : nullptr, nullptr, cf)))
                         return rc;
-                if ((rc = slab_signal(g))) return rc;
                 size_t t = cur; cur = oth; oth = t;
             }
             if (cur != u_off)
@@ -907,6 +864,71 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         MG_LAUNCH_CHECK(c);
         return MG_OK;
     }
+    // ------------------------------------------------------------ Krylov comparator (mg_krylov.cuh)
+    int linf_norm(mg_ctx *c, const void *field, size_t n, double *out) override
+    {
+        k_absmax_partial<R><<<c->npartial, 256, 0, c->stream>>>((const R *)field, n, c->d_partial);
+        MG_LAUNCH_CHECK(c);
+        k_cg_reduce<<<1, 1024, 0, c->stream>>>(c->d_partial, c->npartial, c->d_scalar, 0, 1);
+        MG_LAUNCH_CHECK(c);
+        MG_CK(c, cudaMemcpyAsync(c->h_scalar, c->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+        MG_CK(c, cudaStreamSynchronize(c->stream));
+        *out = *c->h_scalar;
+        return MG_OK;
+    }
+    // x = psi (initial guess as found, the experiment uses -f = initCells' psi), b = f
+    int cg(mg_ctx *c, int max_iter, double epsilon, double *err_hist, double *linf_hist, int *n_done) override
+    {
+        if (c->group) return c->fail(MG_EUNSUPPORTED, "mg_cg: single-GPU only");
+        const int top = c->nlevels - 1, L = c->size;
+        const size_t n = c->N;
+        if (!c->cg_tmp) MG_CK(c, cudaMalloc(&c->cg_tmp, n * c->elem + 2 * sizeof(double) * (size_t)c->npartial + sizeof(double) * CG_NSCAL));
+        R *x = (R *)c->psi, *r = (R *)c->W[top], *p = (R *)c->psiOld, *Ap = (R *)c->cg_tmp;
+        const R *b = (const R *)c->f;
+        double *part2 = (double *)((char *)c->cg_tmp + n * c->elem), *scal = part2 + 2 * c->npartial;
+        double *partA = c->d_partial, *partB = part2;
+        const A inv_h2 = make_coef<A>(DIM, 1.0 / L).inv_h2;
+        const int nb = c->npartial;
+        auto reduce = [&](double *part, int slot, int is_max) {
+            k_cg_reduce<<<1, 1024, 0, c->stream>>>(part, nb, scal, slot, is_max);
+            c->count_launch();
+        };
+        k_cg_init<R, A, DIM><<<nb, 256, 0, c->stream>>>(r, p, x, b, L, inv_h2, partA, partB);
+        MG_LAUNCH_CHECK(c);
+        reduce(partA, CG_RR, 0);
+        reduce(partB, CG_BB, 0);
+        double h[CG_NSCAL];
+        MG_CK(c, cudaMemcpyAsync(h, scal, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+        MG_CK(c, cudaStreamSynchronize(c->stream));
+        const double bb = h[CG_BB] == 0 ? 1.0 : h[CG_BB];
+        int it = 0;
+        double err = std::sqrt(h[CG_RR] / bb);
+        if (!(err < epsilon)) {
+            for (it = 1; it <= max_iter; ++it) {
+                k_cg_apply<R, A, DIM><<<nb, 256, 0, c->stream>>>(Ap, p, L, inv_h2, partA);
+                MG_LAUNCH_CHECK(c);
+                reduce(partA, CG_PAP, 0);
+                k_cg_update<R, A><<<nb, 256, 0, c->stream>>>(x, r, p, Ap, n, scal, partA, partB);
+                MG_LAUNCH_CHECK(c);
+                reduce(partA, CG_RRNEW, 0);
+                reduce(partB, CG_XMAX, 1);
+                MG_CK(c, cudaMemcpyAsync(h, scal, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+                MG_CK(c, cudaStreamSynchronize(c->stream));
+                err = std::sqrt(h[CG_RRNEW] / bb);
+                if (err_hist) err_hist[it - 1] = err;
+                if (linf_hist) linf_hist[it - 1] = h[CG_XMAX];
+                if (err < epsilon || !std::isfinite(err)) break;
+                k_cg_direction<R, A><<<nb, 256, 0, c->stream>>>(p, r, n, scal);
+                MG_LAUNCH_CHECK(c);
+                k_cg_shift<<<1, 1, 0, c->stream>>>(scal);
+                c->count_launch();
+            }
+            if (it > max_iter) it = max_iter;
+        }
+        if (n_done) *n_done = it;
+        return MG_OK;
+    }
+
     int residual_norm(mg_ctx *c, double *rms) override
     {
         if (c->group) return c->fail(MG_EUNSUPPORTED, "mg_residual_norm: not available on slabs yet");
@@ -1043,6 +1065,8 @@ inline void mg_ctx::release()
     if (arena) cudaFree(arena);
     if (debug_arena) cudaFree(debug_arena);
     if (d_partial) cudaFree(d_partial);
+    if (cg_tmp) cudaFree(cg_tmp);
+    cg_tmp = nullptr;
     if (h_scalar) cudaFreeHost(h_scalar);
     if (own_stream) cudaStreamDestroy(own_stream);
     if (cap_stream) cudaStreamDestroy(cap_stream);

@@ -1,0 +1,139 @@
+// mg_krylov.cuh -- conjugate gradient on the reference's Poisson operator, the comparator of
+// test/converge-multigrid-vs-krylov.lua (BASELINE config 5).
+//
+// Operator (converge-multigrid-vs-krylov.lua:48-58, cpu.lua:114-120):
+//     A(u) = (u_xl + u_xr + u_yl + u_yr - 4 u) / h^2,  neighbours outside the grid read 0,  h = 1/width
+// (3-D: six neighbours, -6 u). The experiment calls solver.conjgrad{A=A, b=f, x=-f} (:40-46) and
+// records ||x||_inf per iteration (:62-64). `solver.conjgrad` is an UN-VENDORED dependency of the
+// reference (thenumbernine/lua-solver, no version pinned), so the iteration below is the textbook
+// CG with err = ||r||_2 / ||b||_2 -- PARITY UNPINNED; it is checked against the oracle's restatement
+// of the same textbook algorithm (dot products differ only in summation order).
+//
+// Three launches per iteration, each a single pass over the vectors with its reductions fused in
+// (warp-shuffle block sums, deterministic second stage):
+//   k_cg_apply     Ap = A(p),                 partial p.Ap
+//   k_cg_update    x += alpha p, r -= alpha Ap, partial r.r and max|x|   (alpha from device scalars)
+//   k_cg_direction p = r + beta p                                       (beta  from device scalars)
+#pragma once
+#include "mg_math.cuh"
+#include "mg_ops_ref.cuh"
+
+namespace mg {
+
+// scalars (double) kept on the device between launches
+enum { CG_RR = 0, CG_PAP = 1, CG_RRNEW = 2, CG_XMAX = 3, CG_BB = 4, CG_NSCAL = 8 };
+
+template <int DIM, typename R, typename A>
+__device__ __forceinline__ A apply_A_point(const R *u, int i, int j, int k, int L, size_t idx, A inv_h2)
+{
+    const A S = stencil_sum<DIM, R, A>(u, i, j, k, L, idx);
+    const A d = Ar<A>::sub(S, Ar<A>::mul(DIM == 2 ? (A)4 : (A)6, (A)u[idx]));
+    return Ar<A>::mul(d, inv_h2);   // h^2 is a power of two: identical to the reference's division
+}
+
+__device__ __forceinline__ double block_max(double v)
+{
+    __shared__ double wm[32];
+    int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    if (lane == 0) wm[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        int nw = (blockDim.x + 31) >> 5;
+        v = lane < nw ? wm[lane] : 0.0;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) v = fmax(v, __shfl_down_sync(0xffffffffu, v, o));
+    }
+    return v;
+}
+
+// r = b - A(x); p = r; partial r.r and b.b
+template <typename R, typename A, int DIM>
+__global__ void k_cg_init(R *__restrict__ r, R *__restrict__ p, const R *__restrict__ x, const R *__restrict__ b,
+                          int L, A inv_h2, double *__restrict__ part_rr, double *__restrict__ part_bb)
+{
+    const size_t n = (size_t)L * L * (DIM == 3 ? (size_t)L : 1);
+    double rr = 0, bb = 0;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % L), j = (int)((idx / L) % L), k = DIM == 3 ? (int)(idx / ((size_t)L * L)) : 0;
+        const A rv = Ar<A>::sub((A)b[idx], apply_A_point<DIM, R, A>(x, i, j, k, L, idx, inv_h2));
+        r[idx] = (R)rv;
+        p[idx] = (R)rv;
+        const double rd = (double)(R)rv, bd = (double)b[idx];
+        rr += rd * rd;
+        bb += bd * bd;
+    }
+    rr = block_sum(rr);
+    __syncthreads();
+    bb = block_sum(bb);
+    if (threadIdx.x == 0) { part_rr[blockIdx.x] = rr; part_bb[blockIdx.x] = bb; }
+}
+
+template <typename R, typename A, int DIM>
+__global__ void k_cg_apply(R *__restrict__ Ap, const R *__restrict__ p, int L, A inv_h2, double *__restrict__ part)
+{
+    const size_t n = (size_t)L * L * (DIM == 3 ? (size_t)L : 1);
+    double acc = 0;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % L), j = (int)((idx / L) % L), k = DIM == 3 ? (int)(idx / ((size_t)L * L)) : 0;
+        const R v = (R)apply_A_point<DIM, R, A>(p, i, j, k, L, idx, inv_h2);
+        Ap[idx] = v;
+        acc += (double)p[idx] * (double)v;
+    }
+    acc = block_sum(acc);
+    if (threadIdx.x == 0) part[blockIdx.x] = acc;
+}
+
+template <typename R, typename A>
+__global__ void k_cg_update(R *__restrict__ x, R *__restrict__ r, const R *__restrict__ p, const R *__restrict__ Ap,
+                            size_t n, const double *__restrict__ scal, double *__restrict__ part_rr,
+                            double *__restrict__ part_max)
+{
+    const A alpha = (A)(scal[CG_RR] / scal[CG_PAP]);
+    double rr = 0, mx = 0;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
+        const R xv = (R)Ar<A>::fma(alpha, (A)p[idx], (A)x[idx]);
+        const R rv = (R)Ar<A>::fma(-alpha, (A)Ap[idx], (A)r[idx]);
+        x[idx] = xv;
+        r[idx] = rv;
+        rr += (double)rv * (double)rv;
+        mx = fmax(mx, fabs((double)xv));
+    }
+    rr = block_sum(rr);
+    __syncthreads();
+    mx = block_max(mx);
+    if (threadIdx.x == 0) { part_rr[blockIdx.x] = rr; part_max[blockIdx.x] = mx; }
+}
+
+template <typename R, typename A>
+__global__ void k_cg_direction(R *__restrict__ p, const R *__restrict__ r, size_t n, const double *__restrict__ scal)
+{
+    const A beta = (A)(scal[CG_RRNEW] / scal[CG_RR]);
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x)
+        p[idx] = (R)Ar<A>::fma(beta, (A)p[idx], (A)r[idx]);
+}
+
+// second reduction stage: sum (or max) of the per-block partials into scal[slot]
+__global__ void k_cg_reduce(const double *__restrict__ part, int np, double *__restrict__ scal, int slot, int is_max)
+{
+    double acc = 0;
+    for (int i = threadIdx.x; i < np; i += blockDim.x) acc = is_max ? fmax(acc, part[i]) : acc + part[i];
+    acc = is_max ? block_max(acc) : block_sum(acc);
+    if (threadIdx.x == 0) scal[slot] = acc;
+}
+// after an iteration: rr <- rr_new
+__global__ void k_cg_shift(double *scal) { scal[CG_RR] = scal[CG_RRNEW]; }
+
+// max |field| (the ||psi||_inf the experiment records per multigrid cycle, :25)
+template <typename R>
+__global__ void k_absmax_partial(const R *__restrict__ a, size_t n, double *__restrict__ part)
+{
+    double mx = 0;
+    for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x)
+        mx = fmax(mx, fabs((double)a[idx]));
+    mx = block_max(mx);
+    if (threadIdx.x == 0) part[blockIdx.x] = mx;
+}
+
+}  // namespace mg

@@ -157,7 +157,6 @@ template <typename R> struct Stream3DArgs {
     const R *Vp;      // PRO: coarse correction Vs[L/2]
     R *Rout;          // RES: Rs[L/2]
     int L;            // level width
-    int TZ;           // unused (kept for ABI stability of the args block)
     int flags;        // debug: bit 0 = never take the steady-state body, bit 1 = always mask
     // slab view (multi-GPU): the arrays hold planes [0, nplanes) of which [nz_lo, nz_hi) are
     // owned (written) by this rank; the global grid occupies local planes [zdom0, zdom1).

@@ -113,6 +113,16 @@ int mg_smooth_residual_restrict(mg_ctx *ctx, int L, void *u, const void *f, doub
 int mg_prolong_add_smooth(mg_ctx *ctx, int L, void *u, const void *f, double h, int n,
                           const void *V);
 
+/* ---- Krylov comparator of test/converge-multigrid-vs-krylov.lua:38-69 (SURVEY 8(f) rank 2).
+ * Conjugate gradient on the reference's operator A(u) = (sum of neighbours - 4u)/h^2 (:48-58;
+ * 3-D: six neighbours, -6u) with b = f and x = psi as found (the experiment starts from -f, which
+ * is what initCells leaves in psi). err = ||r||_2/||b||_2 per iteration goes to err_hist, ||x||_inf
+ * (what the experiment plots, :62-64) to linf_hist; stops at err < epsilon or max_iter. The
+ * reference's `solver.conjgrad` is an un-vendored, unpinned dependency: parity unpinned.
+ * mg_linf_norm: ||field||_inf, the quantity the experiment records per multigrid cycle (:25). */
+int mg_cg(mg_ctx *ctx, int max_iter, double epsilon, double *err_hist, double *linf_hist, int *n_done);
+int mg_linf_norm(mg_ctx *ctx, int which, int level, double *out);
+
 /* ---- stage trace: the reference's `debugging` dumps (cpu-raw.lua:126-140) as records.
  * Only MG_MODE_REFSEQ records. name is one of 'f','u','r','R','V','v'. */
 int mg_trace_enable(mg_ctx *ctx, int on);

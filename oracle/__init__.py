@@ -69,6 +69,8 @@ def lib():
         L.orc_op_add_to.argtypes = [i, sz, vp, vp, i]
         L.orc_op_rel_err.argtypes = [i, sz, vp, vp, vp]
         L.orc_op_frob_err.argtypes = [i, i, i, vp, vp, vp, C.POINTER(d)]
+        L.orc_op_apply_A.argtypes = [i, i, i, vp, vp]
+        L.orc_op_cg.argtypes = [i, i, i, vp, vp, i, d, C.POINTER(d), C.POINTER(d), C.POINTER(i)]
         L.orc_max_threads.restype = i
         _lib = L
     return _lib
@@ -137,6 +139,23 @@ def frob_err(dim, real_kind, psi, psiOld):
     assert lib().orc_op_frob_err(dim, real_kind, psi.shape[-1], _ptr(eb), _ptr(psi), _ptr(psiOld),
                                  C.byref(err)) == 0
     return err.value, eb
+
+
+def apply_A(dim, real_kind, u):
+    out = np.empty_like(u)
+    assert lib().orc_op_apply_A(dim, real_kind, u.shape[-1], _ptr(out), _ptr(u)) == 0
+    return out
+
+
+def conjgrad(dim, real_kind, x0, b, max_iter=1000, epsilon=1e-20):
+    """test/converge-multigrid-vs-krylov.lua:38-69 (textbook CG; the reference's solver lib is un-vendored).
+    Returns (x, errs, linf_of_x)."""
+    x = np.ascontiguousarray(x0).copy()
+    errs, linf = (C.c_double * max(max_iter, 1))(), (C.c_double * max(max_iter, 1))()
+    n = C.c_int()
+    assert lib().orc_op_cg(dim, real_kind, x.shape[-1], _ptr(x), _ptr(np.ascontiguousarray(b)), max_iter, epsilon,
+                           errs, linf, C.byref(n)) == 0
+    return x, [errs[k] for k in range(n.value)], [linf[k] for k in range(n.value)]
 
 
 # ------------------------------------------------------------------ solver object

@@ -32,6 +32,7 @@
  *   inPlaceIterativeSolver cpu-raw.lua:176-184 -> orc_in_place_solver
  *   twoGrid          cpu-raw.lua:186-237     -> orc_two_grid
  *   run              cpu-raw.lua:239-258     -> orc_run
+ *   A + conjgrad call test/converge-multigrid-vs-krylov.lua:38-69 -> orc_apply_A, orc_cg (solver lib un-vendored)
  *
  * Threads: `nthreads` > 1 parallelises the order-independent loops (Jacobi, residual,
  * restriction, prolongation, add) with OpenMP; results are bit-identical to 1 thread
@@ -196,6 +197,23 @@ int orc_op_frob_err(int dim, int real_kind, int size, void *errorBuf, const void
     ORC_DISPATCH(real_kind, CALL)
 #undef CALL
     return 0;
+}
+
+int orc_op_apply_A(int dim, int real_kind, int L, void *out, const void *u)
+{
+#define CALL(sfx, T) orc_apply_A##sfx(dim, L, (T *)out, (const T *)u)
+    ORC_DISPATCH(real_kind, CALL)
+#undef CALL
+    return 0;
+}
+int orc_op_cg(int dim, int real_kind, int L, void *x, const void *b, int max_iter, double epsilon,
+              double *err_hist, double *linf_hist, int *n_done)
+{
+    int rc = -1;
+#define CALL(sfx, T) rc = orc_cg##sfx(dim, L, (T *)x, (const T *)b, max_iter, epsilon, err_hist, linf_hist, n_done)
+    ORC_DISPATCH(real_kind, CALL)
+#undef CALL
+    return rc;
 }
 
 /* ---------------------------------------------------------------- solver object */

@@ -306,6 +306,81 @@ static double FN(orc_step)(orc_ctx *c)
                             (const REAL *)c->psiOld);
 }
 
+/* Krylov comparator (test infrastructure for mg_cg): textbook conjugate gradient on the operator of
+ * test/converge-multigrid-vs-krylov.lua:48-58, A(u) = (u_xl + u_xr + u_yl + u_yr - 4 u) / h^2, h = 1/width
+ * (3-D: six neighbours, -6 u), b = f, x given (the experiment passes -f, :45-46); err = ||r||_2/||b||_2;
+ * per-iteration ||x||_inf as the experiment records it (:62-64). `solver.conjgrad` itself is an
+ * un-vendored dependency of the reference (thenumbernine/lua-solver, unpinned): PARITY UNPINNED. */
+static void FN(orc_apply_A)(int dim, int L, REAL *out, const REAL *u)
+{
+    const ACC h = (ACC)1 / (ACC)L;
+    const int Lz = dim == 3 ? L : 1;
+    const size_t sL = (size_t)L, sLL = (size_t)L * L;
+    for (int k = 0; k < Lz; ++k)
+        for (int j = 0; j < L; ++j)
+            for (int i = 0; i < L; ++i) {
+                size_t index = (size_t)i + sL * j + sLL * k;
+                ACC u_xl = i > 0 ? (ACC)u[index - 1] : (ACC)0;
+                ACC u_xr = i < L - 1 ? (ACC)u[index + 1] : (ACC)0;
+                ACC u_yl = j > 0 ? (ACC)u[index - sL] : (ACC)0;
+                ACC u_yr = j < L - 1 ? (ACC)u[index + sL] : (ACC)0;
+                ACC v;
+                if (dim == 2) {
+                    v = (u_xl + u_xr + u_yl + u_yr - 4 * (ACC)u[index]) / (h * h);
+                } else {
+                    ACC u_zl = k > 0 ? (ACC)u[index - sLL] : (ACC)0;
+                    ACC u_zr = k < L - 1 ? (ACC)u[index + sLL] : (ACC)0;
+                    v = (u_xl + u_xr + u_yl + u_yr + u_zl + u_zr - 6 * (ACC)u[index]) / (h * h);
+                }
+                out[index] = (REAL)v;
+            }
+}
+
+static int FN(orc_cg)(int dim, int L, REAL *x, const REAL *b, int max_iter, double epsilon, double *err_hist,
+                      double *linf_hist, int *n_done)
+{
+    const size_t n = (size_t)L * L * (dim == 3 ? (size_t)L : 1);
+    REAL *r = (REAL *)malloc(n * sizeof(REAL)), *p = (REAL *)malloc(n * sizeof(REAL)), *Ap = (REAL *)malloc(n * sizeof(REAL));
+    if (!r || !p || !Ap) return -1;
+    FN(orc_apply_A)(dim, L, Ap, x);
+    double rr = 0, bb = 0;
+    for (size_t i = 0; i < n; ++i) {
+        r[i] = (REAL)((ACC)b[i] - (ACC)Ap[i]);
+        p[i] = r[i];
+        rr += (double)r[i] * (double)r[i];
+        bb += (double)b[i] * (double)b[i];
+    }
+    if (bb == 0) bb = 1;
+    int it = 0;
+    double err = sqrt(rr / bb);
+    if (!(err < epsilon)) {
+        for (it = 1; it <= max_iter; ++it) {
+            FN(orc_apply_A)(dim, L, Ap, p);
+            double pAp = 0;
+            for (size_t i = 0; i < n; ++i) pAp += (double)p[i] * (double)Ap[i];
+            const ACC alpha = (ACC)(rr / pAp);
+            double rrn = 0, mx = 0;
+            for (size_t i = 0; i < n; ++i) {
+                x[i] = (REAL)fma((double)alpha, (double)p[i], (double)x[i]);
+                r[i] = (REAL)fma(-(double)alpha, (double)Ap[i], (double)r[i]);
+                rrn += (double)r[i] * (double)r[i];
+                if (fabs((double)x[i]) > mx) mx = fabs((double)x[i]);
+            }
+            err = sqrt(rrn / bb);
+            if (err_hist) err_hist[it - 1] = err;
+            if (linf_hist) linf_hist[it - 1] = mx;
+            if (err < epsilon || !isfinite(err)) break;
+            const ACC beta = (ACC)(rrn / rr);
+            for (size_t i = 0; i < n; ++i) p[i] = (REAL)fma((double)beta, (double)p[i], (double)r[i]);
+            rr = rrn;
+        }
+        if (it > max_iter) it = max_iter;
+    }
+    free(r); free(p); free(Ap);
+    if (n_done) *n_done = it;
+    return 0;
+}
+
 #undef FN
 #undef REAL
 #undef ACC
