@@ -37,6 +37,9 @@
 #ifndef MG_STREAM_SHFL
 #define MG_STREAM_SHFL 1      // x-neighbours across units via warp shuffle (0: 4-byte shared loads)
 #endif
+#ifndef MG_PACKED_F32
+#define MG_PACKED_F32 1       // fp32 stage arithmetic with Blackwell's packed FADD2/FFMA2/FMUL2
+#endif
 #ifndef MG_STEADY_UNROLL
 #define MG_STEADY_UNROLL 2    // unroll factor of the steady-state step loop
 #endif
@@ -44,6 +47,7 @@
 namespace mg {
 
 constexpr int kSteadyUnroll = MG_STEADY_UNROLL;
+constexpr bool kPackedF32 = MG_PACKED_F32 != 0;
 
 // ------------------------------------------------------------------ PTX wrappers
 __device__ __forceinline__ uint32_t smem_u32(const void *p)
@@ -415,6 +419,63 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
             }
 
             A tot[NP], o[NP];
+            if constexpr (kPackedF32 && std::is_same<A, float>::value && std::is_same<R, float>::value) {
+                // Blackwell packed fp32 (FADD2 / FFMA2 / FMUL2): two IEEE-rn operations per issue
+                // slot, bit-identical to the scalar form. Points are paired along x inside a vector.
+                auto P = [](float a, float b) { return make_float2(a, b); };
+                const float2 mid0 = P(c0[1], c0[2]), mid1 = P(c1[1], c1[2]);
+                float2 sxx[4];
+                sxx[0] = __fadd2_rn(P(l0, c0[0]), mid0); sxx[1] = __fadd2_rn(mid0, P(c0[3], r0));   // xl + xr
+                sxx[2] = __fadd2_rn(P(l1, c1[0]), mid1); sxx[3] = __fadd2_rn(mid1, P(c1[3], r1));
+                const float2 C[4] = {P(c0[0], c0[1]), P(c0[2], c0[3]), P(c1[0], c1[1]), P(c1[2], c1[3])};
+                const float2 YL[4] = {P(up[0], up[1]), P(up[2], up[3]), C[0], C[1]};
+                const float2 YR[4] = {C[2], C[3], P(dn[0], dn[1]), P(dn[2], dn[3])};
+                const float2 INV = P(cf.inv_h2, cf.inv_h2), NINV = P(-cf.inv_h2, -cf.inv_h2), AD = P(cf.adiag, cf.adiag);
+                const float2 NAD = P(cf.nadiag, cf.nadiag), Y = P(cf.yneg, cf.yneg), M1 = P(-1.f, -1.f);
+                float2 T[4], F[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const float2 part = __fadd2_rn(__fadd2_rn(sxx[k], YL[k]), YR[k]);
+                    const float2 PRV = P(prev[sidx][2 * k], prev[sidx][2 * k + 1]);
+                    T[k] = __fadd2_rn(P(acc[sidx][2 * k], acc[sidx][2 * k + 1]), C[k]);   // pending plane gets its z+1
+                    F[k] = P(fv[2 * k], fv[2 * k + 1]);
+                    if (is_res) {
+                        const float2 au = __fadd2_rn(__fmul2_rn(T[k], INV), __fmul2_rn(AD, PRV));
+                        const float2 rv = __ffma2_rn(au, M1, F[k]);                        // f - au
+                        o[2 * k] = rv.x; o[2 * k + 1] = rv.y;
+                    }
+                    const float2 NA = __fadd2_rn(part, PRV);                               // this plane gets its z-1
+                    acc[sidx][2 * k] = NA.x; acc[sidx][2 * k + 1] = NA.y;
+                    prev[sidx][2 * k] = C[k].x; prev[sidx][2 * k + 1] = C[k].y;
+                    tot[2 * k] = T[k].x; tot[2 * k + 1] = T[k].y;
+                }
+                if (!emit) continue;
+                if (!is_res) {
+                    float2 N[4];
+                    unsigned int m = 0xffffffffu;
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        N[k] = __ffma2_rn(T[k], NINV, F[k]);                               // RN(f - S/h^2)
+                        const unsigned int ka = Ar<float>::guard_key(N[k].x), kb = Ar<float>::guard_key(N[k].y);
+                        m = min(m, min(ka, kb));
+                    }
+                    if (m >= Ar<float>::guard_threshold()) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            const float2 q1 = __fmul2_rn(N[k], Y);
+                            const float2 rr = __ffma2_rn(NAD, q1, N[k]);
+                            const float2 q2 = __ffma2_rn(rr, Y, q1);
+                            o[2 * k] = q2.x; o[2 * k + 1] = q2.y;
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) {
+                            o[2 * k] = Ar<float>::div(N[k].x, cf.adiag);
+                            o[2 * k + 1] = Ar<float>::div(N[k].y, cf.adiag);
+                        }
+                    }
+                }
+            } else {
 #pragma unroll
             for (int i = 0; i < VX; ++i) {
                 {   // row 0 of the unit
@@ -443,6 +504,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < NP; ++i) num[i] = jacobi_num<A>(tot[i], (A)fv[i], cf);
                 div_adiag_group<3, A, NP>(num, o, cf);
+            }
             }
             R outv[NP];
 #pragma unroll
