@@ -423,10 +423,11 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                 // Blackwell packed fp32 (FADD2 / FFMA2 / FMUL2): two IEEE-rn operations per issue
                 // slot, bit-identical to the scalar form. Points are paired along x inside a vector.
                 auto P = [](float a, float b) { return make_float2(a, b); };
-                const float2 mid0 = P(c0[1], c0[2]), mid1 = P(c1[1], c1[2]);
+                // xl + xr pairs operands one element apart, which would cost register moves to pair up:
+                // these four sums per row stay scalar and land directly in aligned pairs
                 float2 sxx[4];
-                sxx[0] = __fadd2_rn(P(l0, c0[0]), mid0); sxx[1] = __fadd2_rn(mid0, P(c0[3], r0));   // xl + xr
-                sxx[2] = __fadd2_rn(P(l1, c1[0]), mid1); sxx[3] = __fadd2_rn(mid1, P(c1[3], r1));
+                sxx[0] = P(__fadd_rn(l0, c0[1]), __fadd_rn(c0[0], c0[2])); sxx[1] = P(__fadd_rn(c0[1], c0[3]), __fadd_rn(c0[2], r0));
+                sxx[2] = P(__fadd_rn(l1, c1[1]), __fadd_rn(c1[0], c1[2])); sxx[3] = P(__fadd_rn(c1[1], c1[3]), __fadd_rn(c1[2], r1));
                 const float2 C[4] = {P(c0[0], c0[1]), P(c0[2], c0[3]), P(c1[0], c1[1]), P(c1[2], c1[3])};
                 const float2 YL[4] = {P(up[0], up[1]), P(up[2], up[3]), C[0], C[1]};
                 const float2 YR[4] = {C[2], C[3], P(dn[0], dn[1]), P(dn[2], dn[3])};
