@@ -25,6 +25,19 @@
 // Cells outside the grid must stay exactly 0 at every stage: in-plane via a per-thread
 // bit mask, whole planes via a CTA-uniform test. Values near the tile edge that lack a
 // neighbour are garbage by construction and never reach the H-deep interior (H = NST).
+//
+// Also in this kernel (details at the code):
+//  * f planes travel through their own TMA ring (2*NST+1 slots); zero fill makes them predicate free.
+//  * fill / steady / drain are separate loops; the steady body has no per-stage predicates and,
+//    on tiles inside the grid, no masks.
+//  * shared-memory rows are 96 floats (fp32 tile 88 x 24): 128-bit accesses are bank-conflict
+//    free; x-neighbours across threads come from warp shuffles.
+//  * fp32 arithmetic is issued as Blackwell packed FADD2 / FFMA2 / FMUL2 (bit-identical per lane).
+//  * work is dealt to one CTA per SM in equal shares of tile x plane-pair units (run_chunk), so
+//    tiles need not divide the grid and there is no tail wave.
+//  * multi-GPU: slab views (local vs global planes), boundary planes stored straight into the
+//    neighbours' ghost planes over NVLink peer memory, and the per-pass handshake
+//    (acquire on entry, last CTA publishes) -- see mg_slab.cuh.
 #pragma once
 #include <cuda.h>
 #include <cuda_runtime.h>
