@@ -22,6 +22,14 @@
 #include "mg_stream3d.cuh"
 #include "mg_warp2d.cuh"
 
+// In-plane tile of the streaming smoother for 4-byte reals (see launch_stream3d_t).
+#ifndef MG_TILE_X
+#define MG_TILE_X 56
+#endif
+#ifndef MG_TILE_Y
+#define MG_TILE_Y 40
+#endif
+
 namespace mg {
 
 constexpr int MAX_LEVELS = 24;
@@ -333,14 +341,15 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
     // cur + prolong(Vp), followed optionally by Rout = restrict(f - A cur).
     // ---- streaming (TMA, temporally blocked) smoother passes, 3-D only
     // the y extent of the float tile is chosen per launch (see pick_tile_y)
-    static constexpr int kTileX = sizeof(R) == 4 ? 88 : 32;
-    static constexpr int kTileYA = sizeof(R) == 4 ? 24 : 32, kTileYB = kTileYA;   // (88 x 22 tried: see below)
+    static constexpr int kTileX = sizeof(R) == 4 ? MG_TILE_X : 32;
+    static constexpr int kTileYA = sizeof(R) == 4 ? MG_TILE_Y : 32, kTileYB = kTileYA;   // (88 x 22 tried: see below)
     // Lock-step mode: when the tile columns of a level fit the resident CTAs almost exactly
     // (>= 90 %), give every CTA one whole column: all columns then march through z together and
     // the halo rows neighbouring tiles share are served from L2 instead of HBM. At 512^2 planes a
     // tile of 88 x 22 gives 6 x 24 = 144 columns for 148 SMs; 88 x 24 gives 132 (89 %).
-    // MEASURED (round 1, 512^3): lock-step 88 x 22 = 242 V-cycles/s, balanced 88 x 24 = 260: the
-    // passes are not HBM-bound, so the balanced partition stays the default ("lockstep" = 0).
+    // MEASURED (512^3): lock-step 88 x 22 = 242 V-cycles/s against balanced 88 x 24 = 260; again with the
+    // 56 x 40 tile (130 columns): 203 against 325. The passes are not HBM-bound, so the balanced
+    // partition stays the default ("lockstep" = 0).
     static int pick_tile_y(mg_ctx *c, int L, bool *lockstep)
     {
         *lockstep = false;
@@ -370,9 +379,11 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
                           bool lockstep)
     {
         const int L = 1 << lv;
-        // In-plane tile. 4-byte reals: 88 x 24 or 88 x 22 (+ halo = 96 wide): 24 vectors per row and a
-        // 384-byte row pitch, so every quarter-warp of a 128-bit shared-memory access stays inside
-        // one row and is bank-conflict free; tiles need not divide the grid (masks + partition).
+        // In-plane tile. 4-byte reals: 56 x 40 (+ halo = 64 wide): 16 vectors per row and a 256-byte row
+        // pitch, so a warp holds two whole rows of units: every quarter-warp of a 128-bit shared-memory
+        // access stays inside one row (bank-conflict free) and lanes 0 / 31 sit on tile edges, where the
+        // shuffled x-neighbour needs no patch. Tiles need not divide the grid (masks + partition).
+        // (88 x 24, the round-1 tile, measures the same V-cycles/s but needs the edge patches.)
         // 8-byte reals: 32 x 32 (shared-memory budget).
         constexpr int TX = kTileX;
         typedef Stream3DCfg<R, S, RES, TX, TY> C;

@@ -12,13 +12,14 @@
 // mbarrier-signalled, NSLOT-deep ring); TMA's out-of-bounds ZERO FILL is the reference's
 // Dirichlet rule "a neighbour outside the grid reads 0" (cpu-raw.lua:36-39), so domain edges
 // need no branches on load. The S sweeps (+1 residual stage) form a software pipeline of
-// NST stages; at step t stage s consumes plane a_t - 2(s-1) of stage s-1's output from
-// shared memory and emits its own plane one below it. A thread owns VX x 2 columns for the
-// whole launch and keeps, per stage, two registers per column:
-//   prev = centre value of the previous plane            (the z-1 neighbour)
-//   acc  = ((xl+xr)+yl)+yr + zl of the pending plane      (waiting for its z+1 neighbour)
-// so each plane of each stage is read from shared memory exactly once (4 x LDS.128 +
-// 4 x LDS.32 per 8 points) and ONE __syncthreads() per step serves all stages.
+// NST stages; at step t stage s consumes plane a_t - 2(s-1) of stage s-1's output and emits its
+// own plane one below it. A thread owns VX x 2 columns for the whole launch and keeps, per stage:
+//   prev  = centre value of the previous plane            (the z-1 neighbour)
+//   acc   = ((xl+xr)+yl)+yr + zl of the pending plane      (waiting for its z+1 neighbour)
+//   carry = its own output of that stage from the last step (fp32): the next stage's centre rows
+// so of each plane of each stage only the rows ABOVE and BELOW the unit (other threads' values)
+// are read back from the shared-memory ring (2 x LDS.128 per 8 points), x-neighbours come from
+// warp shuffles, and ONE __syncthreads() per step serves all stages.
 // The summation order ((((xl+xr)+yl)+yr)+zl)+zr is preserved, so results are bit-identical
 // to the one-sweep-per-launch kernels (all arithmetic from mg_math.cuh).
 //
@@ -28,10 +29,14 @@
 //
 // Also in this kernel (details at the code):
 //  * f planes travel through their own TMA ring (2*NST+1 slots); zero fill makes them predicate free.
+//    The f plane and the source plane fetched in the same step are counted on ONE mbarrier: a step
+//    has a single wait.
 //  * fill / steady / drain are separate loops; the steady body has no per-stage predicates and,
 //    on tiles inside the grid, no masks.
-//  * shared-memory rows are 96 floats (fp32 tile 88 x 24): 128-bit accesses are bank-conflict
-//    free; x-neighbours across threads come from warp shuffles.
+//  * the fp32 tile is 56 x 40 (+ halo = 64 wide): 16 vectors per row, so a warp holds whole rows of
+//    units, 128-bit accesses are bank-conflict free and the shuffles need no edge patch.
+//  * all shared-memory traffic of the hot loop is addressed as 32-bit shared address + uniform slot
+//    offset + immediate; the global stores follow running pointers.
 //  * fp32 arithmetic is issued as Blackwell packed FADD2 / FFMA2 / FMUL2 (bit-identical per lane).
 //  * work is dealt to one CTA per SM in equal shares of tile x plane-pair units (run_chunk), so
 //    tiles need not divide the grid and there is no tail wave.
@@ -50,6 +55,9 @@
 #ifndef MG_STREAM_SHFL
 #define MG_STREAM_SHFL 1      // x-neighbours across units via warp shuffle (0: 4-byte shared loads)
 #endif
+#ifndef MG_STREAM_CARRY
+#define MG_STREAM_CARRY 1     // fp32: a stage's own output rows reach the next stage through registers
+#endif
 #ifndef MG_PACKED_F32
 #define MG_PACKED_F32 1       // fp32 stage arithmetic with Blackwell's packed FADD2/FFMA2/FMUL2
 #endif
@@ -67,24 +75,23 @@ __device__ __forceinline__ uint32_t smem_u32(const void *p)
 {
     return (uint32_t)__cvta_generic_to_shared(p);
 }
-__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void mbar_inval(uint64_t *bar)
+__device__ __forceinline__ void mbar_inval(uint32_t bar)
 {
-    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+    asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_fence_init()
 {
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 }
-__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
 {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
-                 : "memory");
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
 }
-__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
     asm volatile(
         "{\n"
@@ -94,7 +101,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         "@p bra DONE_%=;\n"
         "bra WAIT_%=;\n"
         "DONE_%=:\n"
-        "}\n" ::"r"(smem_u32(bar)),
+        "}\n" ::"r"(bar),
         "r"(parity)
         : "memory");
 }
@@ -104,28 +111,35 @@ __device__ __forceinline__ void fence_proxy_async_smem()
 {
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
 }
-__device__ __forceinline__ void tma_load_3d(void *smem_dst, const CUtensorMap *map, int x, int y, int z,
-                                            uint64_t *bar)
+__device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap *map, int x, int y, int z, uint32_t bar)
 {
     asm volatile(
         "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes"
-        " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_u32(smem_dst)),
-        "l"(map), "r"(x), "r"(y), "r"(z), "r"(smem_u32(bar))
+        " [%0], [%1, {%2, %3, %4}], [%5];" ::"r"(smem_dst),
+        "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
         : "memory");
 }
 
 // predicated shared-memory load: returns *p if pred, else old (no branch, no access when !pred)
-__device__ __forceinline__ float lds_if(bool pred, const float *p, float old)
+__device__ __forceinline__ float lds_if(bool pred, uint32_t addr, float old)
 {
     asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.shared.f32 %0, [%1];\n}\n"
-                 : "+f"(old) : "r"(smem_u32(p)), "r"((unsigned)pred) : "memory");
+                 : "+f"(old) : "r"(addr), "r"((unsigned)pred));
     return old;
 }
-__device__ __forceinline__ double lds_if(bool pred, const double *p, double old)
+__device__ __forceinline__ double lds_if(bool pred, uint32_t addr, double old)
 {
     asm volatile("{\n.reg .pred q;\nsetp.ne.u32 q, %2, 0;\n@q ld.shared.f64 %0, [%1];\n}\n"
-                 : "+d"(old) : "r"(smem_u32(p)), "r"((unsigned)pred) : "memory");
+                 : "+d"(old) : "r"(addr), "r"((unsigned)pred));
     return old;
+}
+__device__ __forceinline__ float lds1(uint32_t addr, float)
+{
+    float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr)); return v;
+}
+__device__ __forceinline__ double lds1(uint32_t addr, double)
+{
+    double v; asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr)); return v;
 }
 
 // ------------------------------------------------------------------ vector access
@@ -136,6 +150,16 @@ template <> struct Vec<float> {
     static __device__ __forceinline__ void unpack(const T &v, float *o) { o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w; }
     static __device__ __forceinline__ T pack(const float *o) { return make_float4(o[0], o[1], o[2], o[3]); }
     static __device__ __forceinline__ T zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+    // 128-bit shared-memory access by 32-bit shared-window address: LDS/STS [reg + imm], no
+    // generic-to-shared conversion and no re-derivation of the window base per access
+    static __device__ __forceinline__ void lds(uint32_t addr, float *o)
+    {
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(addr));
+    }
+    static __device__ __forceinline__ void sts(uint32_t addr, const float *o)
+    {
+        asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
+    }
 };
 template <> struct Vec<double> {
     static constexpr int N = 2;
@@ -143,6 +167,14 @@ template <> struct Vec<double> {
     static __device__ __forceinline__ void unpack(const T &v, double *o) { o[0] = v.x; o[1] = v.y; }
     static __device__ __forceinline__ T pack(const double *o) { return make_double2(o[0], o[1]); }
     static __device__ __forceinline__ T zero() { return make_double2(0., 0.); }
+    static __device__ __forceinline__ void lds(uint32_t addr, double *o)
+    {
+        asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(addr));
+    }
+    static __device__ __forceinline__ void sts(uint32_t addr, const double *o)
+    {
+        asm volatile("st.shared.v2.f64 [%0], {%1, %2};" ::"r"(addr), "d"(o[0]), "d"(o[1]) : "memory");
+    }
 };
 
 template <typename R, int S, bool RES, int TX, int TY> struct Stream3DCfg {
@@ -154,19 +186,25 @@ template <typename R, int S, bool RES, int TX, int TY> struct Stream3DCfg {
     static constexpr int WX = TX + 2 * HX, WY = TY + 2 * HY;
     static constexpr int UX = WX / VX, UY = WY / 2;
     static constexpr int NT = UX * UY;
+    // a warp holds whole rows of units: lanes 0 / 31 sit on a tile edge, where the missing x-neighbour
+    // lies in the garbage zone anyway, so the shuffles need no shared-memory patch
+    static constexpr bool EDGE_FREE = (32 % UX) == 0;
     static constexpr int NTHREADS = (NT + 31) / 32 * 32;
     static constexpr int PLANE = WX * WY;
     static constexpr int PLANE_BYTES = PLANE * (int)sizeof(R);
     static constexpr int SLOT_BYTES = (PLANE_BYTES + 127) / 128 * 128;
     static constexpr int SLOT_ELEMS = SLOT_BYTES / (int)sizeof(R);
-    static constexpr int NSLOT = 3;         // source-plane ring (TMA prefetch distance NSLOT-1 steps)
+    static constexpr int NSLOT = 3;         // source-plane ring (TMA prefetch distance NSLOT-1 = 2 steps, like f)
     static constexpr int NRING = NST - 1;   // intermediate stage outputs, double buffered
     static constexpr int NF = 2 * NST + 1;  // f-plane ring: a plane lives 2*NST-1 steps, fetched 2 ahead
     static constexpr int NSLOTS_TOTAL = NSLOT + 2 * NRING + NF;
-    static constexpr int SMEM_BYTES = NSLOTS_TOTAL * SLOT_BYTES + (NSLOT + NF) * 8;
+    static constexpr int SMEM_BYTES = NSLOTS_TOTAL * SLOT_BYTES + NSLOT * 8;   // slots + the source ring's mbarriers
+    static_assert(NSLOT == 3, "source plane t+2 and f plane t+1 are fetched together and share an mbarrier");
     static_assert(TX % VX == 0 && TY % 2 == 0 && WY % 2 == 0, "tile shape");
     static_assert(NTHREADS <= 1024, "too many threads");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
+    // two CTAs per SM when the shared memory (plus the 1 KB the system reserves per CTA) allows it
+    static constexpr int MIN_CTAS = 2 * (SMEM_BYTES + 1024) <= 233472 && 2 * NTHREADS <= 1024 ? 2 : 1;
 };
 
 template <typename R> struct Stream3DArgs {
@@ -207,7 +245,7 @@ __device__ __forceinline__ void s3_st_release_sys(unsigned long long *p, unsigne
 }
 
 template <typename R, typename A, int S, bool PRO, bool RES, int TX, int TY>
-__global__ void __launch_bounds__((Stream3DCfg<R, S, RES, TX, TY>::NTHREADS), 1)
+__global__ void __launch_bounds__((Stream3DCfg<R, S, RES, TX, TY>::NTHREADS), (Stream3DCfg<R, S, RES, TX, TY>::MIN_CTAS))
 k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap f_map,
            Stream3DArgs<R> a, Coef<A> cf)
 {
@@ -217,15 +255,16 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
 
     // layout: [NSLOT source slots][NRING*2 stage slots][NF f slots][mbarriers]. The dynamic
     // shared window starts at offset 0 of the CTA's shared memory (no static __shared__ in
-    // this kernel), so every slot is 128-byte aligned as TMA requires. Pointers are derived
-    // from the __shared__ array itself so that accesses compile to LDS/STS.
+    // this kernel), so every slot is 128-byte aligned as TMA requires. All shared-memory
+    // traffic of the hot loop is addressed by 32-bit shared-window addresses
+    // (per-thread base + slot offset + immediate): one LDS/STS each, no address rebuilding.
     extern __shared__ __align__(1024) unsigned char smem_raw[];
-    R *const sm = reinterpret_cast<R *>(smem_raw);
-    auto in_slot = [&](int k) -> R * { return sm + k * C::SLOT_ELEMS; };
-    auto ring_slot = [&](int s, int par) -> R * { return sm + (NSLOT + 2 * s + par) * C::SLOT_ELEMS; };
-    auto f_slot = [&](int k) -> R * { return sm + (NSLOT + 2 * C::NRING + k) * C::SLOT_ELEMS; };
-    uint64_t *const mbar_u = reinterpret_cast<uint64_t *>(smem_raw + (size_t)C::NSLOTS_TOTAL * C::SLOT_BYTES);
-    uint64_t *const mbar_f = mbar_u + NSLOT;
+    constexpr uint32_t SB = (uint32_t)C::SLOT_BYTES, ROWB = (uint32_t)(C::WX * sizeof(R));
+    constexpr uint32_t RING0 = NSLOT * SB, F0 = (NSLOT + 2 * C::NRING) * SB;
+    const uint32_t sbase = smem_u32(smem_raw);
+    // One mbarrier per source slot. The f plane fetched together with a source plane (same step, needed at
+    // the same later step) is counted on the SAME mbarrier, so a step has a single wait.
+    const uint32_t mb_u = sbase + (uint32_t)C::NSLOTS_TOTAL * SB;
 
     const int tid = threadIdx.x, lane = tid & 31;
     const bool worker = tid < C::NT;   // the last warp's spare threads mirror unit 0 and never store
@@ -256,12 +295,12 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     // ---- per-thread geometry (constant over the launch)
     const int gx0 = x0 - C::HX + VX * ux;          // global x of the first owned point
     const int gy0 = y0 - C::HY + 2 * uy;           // global y of the first owned row
-    const int off0 = (2 * uy) * C::WX + VX * ux;   // smem offset of row 0 of the unit
-    const int off1 = off0 + C::WX;
-    const int offU = uy == 0 ? off0 : off0 - C::WX;               // row above (clamped: garbage zone)
-    const int offD = uy == C::UY - 1 ? off1 : off1 + C::WX;       // row below
-    const int dl = ux == 0 ? 0 : -1;                               // left neighbour of the first point
-    const int dr = ux == C::UX - 1 ? VX - 1 : VX;                  // right neighbour of the last point
+    const int off0 = (2 * uy) * C::WX + VX * ux;   // element offset of row 0 of the unit inside a slot
+    const uint32_t a0 = sbase + (uint32_t)off0 * (uint32_t)sizeof(R);   // row 0 of the unit in slot 0; row 1 = + ROWB
+    const uint32_t aU = uy == 0 ? a0 : a0 - ROWB;                       // row above (clamped: garbage zone)
+    const uint32_t aD = uy == C::UY - 1 ? a0 + ROWB : a0 + 2 * ROWB;    // row below
+    const uint32_t aL = ux == 0 ? a0 : a0 - (uint32_t)sizeof(R);        // left neighbour of the first point
+    const uint32_t aR = a0 + (uint32_t)((ux == C::UX - 1 ? VX - 1 : VX) * sizeof(R));   // right neighbour of the last
     const bool xin = gx0 >= 0 && gx0 < L;                          // L % VX == 0: whole group in or out
     const bool yin0 = gy0 >= 0 && gy0 < L, yin1 = gy0 + 1 >= 0 && gy0 + 1 < L;
     const bool in0 = worker && xin && yin0, in1 = worker && xin && yin1;
@@ -271,15 +310,24 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     const bool st1 = in1 && xint && (2 * uy + 1 >= C::HY) && (2 * uy + 1 < C::HY + TY);
     const size_t sL = (size_t)L, sLL = sL * sL;
     R *const dst0 = a.dst + ((size_t)gx0 + sL * (size_t)gy0);      // dereferenced only when in-domain
+    int stm = (st0 ? 1 : 0) | (st1 ? 2 : 0);                       // which rows of the unit this thread writes
+    asm volatile("" : "+r"(stm));   // opaque: kept in a register instead of being re-derived from tid every step
+    const bool has_peer = a.peer_lo != nullptr || a.peer_hi != nullptr;
+    // running output pointer of the last Jacobi stage: it emits plane zb + t - 2*(S-1) - 1 at step t
+    R *dcur = reinterpret_cast<R *>(reinterpret_cast<intptr_t>(dst0) +
+                                    (intptr_t)sizeof(R) * (intptr_t)sLL * (intptr_t)(zb - 2 * (S - 1) - 1));
+    // RES: running offset of the unit's coarse row inside Rout (first store: fine plane z0 + 1)
+    size_t rcur = (size_t)(gx0 >> 1) + (size_t)(L >> 1) * ((size_t)(gy0 >> 1) +
+                  (size_t)(L >> 1) * (size_t)(((z0 - a.nz_lo) >> 1) + a.rz_off));
     // the whole (tile + halo) footprint lies inside the grid in x and y: no in-plane masking
     const bool cta_inner = (x0 - C::HX >= 0) && (x0 + TX + C::HX <= L) && (y0 - C::HY >= 0) && (y0 + TY + C::HY <= L);
 
     __syncthreads();  // every thread is done with the previous chunk's shared memory
     if (tid == 0) {
 #pragma unroll
-        for (int k = 0; k < NSLOT + NF; ++k) {
-            if (!first_chunk) mbar_inval(&mbar_u[k]);   // all of its transfers were awaited
-            mbar_init(&mbar_u[k], 1);                   // mbar_f follows mbar_u in memory
+        for (int k = 0; k < NSLOT; ++k) {
+            if (!first_chunk) mbar_inval(mb_u + 8 * k);   // all of its transfers were awaited
+            mbar_init(mb_u + 8 * k, 1);
         }
         mbar_fence_init();
     }
@@ -288,16 +336,16 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     if (tid == 0) {
 #pragma unroll
         for (int k = 0; k < NSLOT - 1; ++k)
-            if (k < nin) {
-                mbar_expect_tx(&mbar_u[k], C::PLANE_BYTES);
-                tma_load_3d(in_slot(k), &src_map, x0 - C::HX, y0 - C::HY, zb + k, &mbar_u[k]);
+            if (k < nin) {      // nin >= 4: planes 0 and 1 always exist
+                mbar_expect_tx(mb_u + 8 * k, k == 1 ? 2 * C::PLANE_BYTES : C::PLANE_BYTES);
+                tma_load_3d(sbase + k * SB, &src_map, x0 - C::HX, y0 - C::HY, zb + k, mb_u + 8 * k);
             }
         // f plane j (global z = zb + j) is first needed at step j + 1 (stage 1) and last at step
-        // j + 2*NST - 1 (stage NST); it is fetched at step j - 1, when the slot's previous tenant
-        // j - NF retired (step j - 2). Plane 0 is never used but is fetched here so that every
-        // slot sees its planes in order (uniform mbarrier phases).
-        mbar_expect_tx(&mbar_f[0], C::PLANE_BYTES);
-        tma_load_3d(f_slot(0), &f_map, x0 - C::HX, y0 - C::HY, zb, &mbar_f[0]);
+        // j + 2*NST - 1 (stage NST); it is fetched at step j - 1 together with source plane j + 1, when
+        // the slot's previous tenant j - NF retired (step j - 2), and it is counted on that source
+        // plane's mbarrier (awaited at step j + 1). Plane 0 is never used but is fetched here, with
+        // source plane 1, so that every slot sees its planes in order.
+        tma_load_3d(sbase + F0, &f_map, x0 - C::HX, y0 - C::HY, zb, mb_u + 8);
     }
 
     // PRO: add prolong(V) to the own points of an arrived source slot, in place. The coarse
@@ -321,18 +369,17 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
             for (int i = 0; i < VX / 2; ++i) vpre[r][i] = in ? a.Vp[crow + i] : (R)0;
         }
     };
-    auto fix_apply = [&](int slot) {
+    auto fix_apply = [&](uint32_t slot_off) {
         if (!PRO || !vpre_on) return;
-        R *sl = in_slot(slot);
 #pragma unroll
         for (int r = 0; r < 2; ++r) {
             const bool in = r == 0 ? in0 : in1;
             if (!in) continue;
             R u[VX];
-            Vec<R>::unpack(*(const VT *)(sl + (r == 0 ? off0 : off1)), u);
+            Vec<R>::lds(a0 + slot_off + r * ROWB, u);
 #pragma unroll
             for (int i = 0; i < VX; ++i) u[i] = (R)Ar<A>::add((A)u[i], (A)vpre[r][i >> 1]);
-            *(VT *)(sl + (r == 0 ? off0 : off1)) = Vec<R>::pack(u);
+            Vec<R>::sts(a0 + slot_off + r * ROWB, u);
         }
     };
 
@@ -341,21 +388,32 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     for (int s = 0; s < NST; ++s)
 #pragma unroll
         for (int i = 0; i < NP; ++i) { acc[s][i] = (A)0; prev[s][i] = (A)0; }
+    // carry[s] = the unit's own output of stage s+1 from the previous step: the centre rows of
+    // stage s+2 this step. Only the rows ABOVE and BELOW the unit (other threads' values) are read
+    // back from the shared-memory ring.
+    // (fp32 arithmetic only: with 8-byte accumulators the extra registers would spill.)
+    constexpr bool CARRY = MG_STREAM_CARRY && sizeof(A) == 4;
+    R carry[CARRY && NST > 1 ? NST - 1 : 1][NP];
+#pragma unroll
+    for (int s = 0; s < (CARRY && NST > 1 ? NST - 1 : 1); ++s)
+#pragma unroll
+        for (int i = 0; i < NP; ++i) carry[s][i] = (R)0;
     A rpart[VX / 2 > 0 ? VX / 2 : 1];  // RES: restriction partial sums of the even plane
 #pragma unroll
     for (int i = 0; i < VX / 2; ++i) rpart[i] = (A)0;
 
     if (PRO) {
         fix_load(0);
-        mbar_wait(&mbar_u[0], 0);
+        mbar_wait(mb_u, 0);
         fix_apply(0);
         __syncthreads();
     }
 
-    // ring cursors, advanced once per step (no integer division in the loop)
+    // ring cursors, advanced once per step (no integer division in the loop); bu / bfq are the
+    // same cursors as byte offsets
     int su = 0, pu = 0;        // source slot of step t = t % NSLOT, and its mbarrier parity
-    int sf = NF - 1, pf = 1;   // slot/parity of f plane j = t - 1 (stage 1's plane); j = -1 at t = 0
-    // (sf, pf) track j = t - 1: j = -1 -> slot NF-1 of "phase -1" (parity 1); becomes (0, 0) at t = 1
+    int sf = NF - 1;           // slot of f plane j = t - 1 (stage 1's plane); j = -1 at t = 0 -> becomes 0 at t = 1
+    uint32_t bu = 0, bfq = (NF - 1) * SB;
 
     // One pipeline step. STEADY: every stage is active, emits, and every emitted plane is inside
     // the grid and (for the last Jacobi stage) inside [z0, z1): no per-stage predicates.
@@ -364,95 +422,184 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         constexpr bool ST = decltype(steady_tag)::value, MK = decltype(masked_tag)::value;
         // (1) refill: the source slot consumed at step t-1 and the f slot retired at step t-1
         if (tid == 0) {
-            const int k = t + NSLOT - 1;
+            const int k = t + NSLOT - 1;                      // source plane needed at step t + NSLOT - 1
             if (k < nin) {
                 const int ks = su == 0 ? NSLOT - 1 : su - 1;  // (t + NSLOT - 1) % NSLOT
-                fence_proxy_async_smem();
-                mbar_expect_tx(&mbar_u[ks], C::PLANE_BYTES);
-                tma_load_3d(in_slot(ks), &src_map, x0 - C::HX, y0 - C::HY, zb + k, &mbar_u[ks]);
-            }
-            const int j = t + 1;                              // f plane stage 1 needs at step t + 2
-            if (j <= nin - 2) {
+                const int j = t + 1;                          // f plane stage 1 needs at step t + 2
                 int ksf = sf + 2; if (ksf >= NF) ksf -= NF;   // (t + 1) % NF  (sf = (t - 1) % NF)
-                mbar_expect_tx(&mbar_f[ksf], C::PLANE_BYTES);
-                tma_load_3d(f_slot(ksf), &f_map, x0 - C::HX, y0 - C::HY, zb + j, &mbar_f[ksf]);
+                // The slots being refilled were last READ through the generic proxy before the barrier that ended
+                // step t-1 (the values are in registers). Only PRO also WROTE the source slot (fix_apply):
+                // order those writes before the async-proxy refill.
+                if (PRO) fence_proxy_async_smem();
+                mbar_expect_tx(mb_u + 8 * ks, 2 * C::PLANE_BYTES);
+                tma_load_3d(sbase + ks * SB, &src_map, x0 - C::HX, y0 - C::HY, zb + k, mb_u + 8 * ks);
+                tma_load_3d(sbase + F0 + ksf * SB, &f_map, x0 - C::HX, y0 - C::HY, zb + j, mb_u + 8 * ks);
             }
         }
         if (PRO && t + 1 < nin) fix_load(t + 1);
         // (2) source plane of this step (PRO: it was awaited and fixed up during step t-1)
         if (!PRO) {
-            if (ST || t < nin) mbar_wait(&mbar_u[su], (uint32_t)pu);
+            if (ST || t < nin) mbar_wait(mb_u + 8 * su, (uint32_t)pu);
         }
-        // (3) the pipeline stages; stage s = sidx + 1
-#pragma unroll
-        for (int sidx = 0; sidx < NST; ++sidx) {
-            const int s = sidx + 1;
-            if (!ST) {
-                const bool active = (t >= 3 * sidx) && (t <= nin + s - 2);
-                if (!active) continue;
-            }
-            const bool emit = ST ? true : (t >= 3 * s - 1);
-            const int p = zb + t - 2 * sidx - 1;                   // plane emitted (q - 1)
-            const R *in = sidx == 0 ? in_slot(su) : ring_slot(sidx - 1, (t - 1) & 1);
-            const bool is_res = RES && s == NST;
-            const bool last_jacobi = s == S;
-            const bool pin = ST ? true : (p >= zdom0 && p < zdom1);
-
+        // (3) the pipeline stages. The stages of one step are independent of each other (each reads
+        // what was written a step earlier), so they may run in any order, except that stage s+1 must
+        // take its centre rows from the carry registers before stage s refills them.
+        struct In { R c0[VX], c1[VX], up[VX], dn[VX], l0, l1, r0, r1, fv[NP]; };
+        auto stage_p = [&](int sidx) { return zb + t - 2 * sidx - 1; };      // plane emitted (q - 1)
+        auto stage_active = [&](int sidx) { return ST ? true : ((t >= 3 * sidx) && (t <= nin + sidx - 1)); };
+        auto stage_emit = [&](int sidx) { return ST ? true : (t >= 3 * sidx + 2); };
+        // everything stage sidx+1 reads this step: centre rows (source slot or carry), the rows above and
+        // below from the plane stage sidx wrote into the ring a step ago, x-neighbours by shuffle, and f
+        auto load_inputs = [&](int sidx, bool emit, In &q) {
+            // input plane: this step's source slot, or the ring slot stage s-1 wrote during step t-1
+            const uint32_t ib = sidx == 0 ? bu : RING0 + (uint32_t)(2 * (sidx - 1) + ((t - 1) & 1)) * SB;
             // f of the emitted plane, from the f ring (TMA zero fill covers everything outside the grid)
-            R fv[NP];
             if (emit) {
-                int kf = sf - 2 * sidx; if (kf < 0) kf += NF;      // (t - 1 - 2*sidx) % NF
-                if (sidx == 0) mbar_wait(&mbar_f[kf], (uint32_t)pf);
-                const R *fs = f_slot(kf);
-                Vec<R>::unpack(*(const VT *)(fs + off0), fv);
-                Vec<R>::unpack(*(const VT *)(fs + off1), fv + VX);
+                uint32_t fb = bfq - (uint32_t)(2 * sidx) * SB;     // slot (t - 1 - 2*sidx) % NF
+                if ((int)fb < 0) fb += NF * SB;
+                Vec<R>::lds(a0 + F0 + fb, q.fv);
+                Vec<R>::lds(a0 + F0 + fb + ROWB, q.fv + VX);
             } else {
 #pragma unroll
-                for (int i = 0; i < NP; ++i) fv[i] = (R)0;
+                for (int i = 0; i < NP; ++i) q.fv[i] = (R)0;
             }
-
-            R c0[VX], c1[VX], up[VX], dn[VX];
-            Vec<R>::unpack(*(const VT *)(in + off0), c0);
-            Vec<R>::unpack(*(const VT *)(in + off1), c1);
-            Vec<R>::unpack(*(const VT *)(in + offU), up);
-            Vec<R>::unpack(*(const VT *)(in + offD), dn);
-            // x-neighbours across units come from the adjacent lane (warp shuffle) instead of a
-            // 4-byte shared load at 16-byte stride (4-way bank conflict). Lanes 0 / 31 have no such
-            // lane and read shared memory; where the adjacent lane is a different row (ux = 0 or
-            // UX-1) the value is garbage, exactly in the garbage zone of the tile edge.
-            R l0, l1, r0, r1;
-            if (MG_STREAM_SHFL) {
-                l0 = __shfl_up_sync(0xffffffffu, c0[VX - 1], 1); l1 = __shfl_up_sync(0xffffffffu, c1[VX - 1], 1);
-                r0 = __shfl_down_sync(0xffffffffu, c0[0], 1); r1 = __shfl_down_sync(0xffffffffu, c1[0], 1);
-                // lanes 0 / 31 have no such lane: one-lane predicated loads, no branch
-                l0 = lds_if(lane == 0, in + off0 + dl, l0); l1 = lds_if(lane == 0, in + off1 + dl, l1);
-                r0 = lds_if(lane == 31, in + off0 + dr, r0); r1 = lds_if(lane == 31, in + off1 + dr, r1);
+            if (sidx == 0 || !CARRY) {
+                Vec<R>::lds(a0 + ib, q.c0);
+                Vec<R>::lds(a0 + ib + ROWB, q.c1);
             } else {
-                l0 = in[off0 + dl]; l1 = in[off1 + dl]; r0 = in[off0 + dr]; r1 = in[off1 + dr];
+#pragma unroll
+                for (int i = 0; i < VX; ++i) { q.c0[i] = carry[sidx > 0 ? sidx - 1 : 0][i]; q.c1[i] = carry[sidx > 0 ? sidx - 1 : 0][VX + i]; }
             }
+            Vec<R>::lds(aU + ib, q.up);
+            Vec<R>::lds(aD + ib, q.dn);
+            // x-neighbours across units come from the adjacent lane (warp shuffle) instead of a
+            // 4-byte shared load at 16-byte stride (4-way bank conflict). Where the adjacent lane is a
+            // different row (ux = 0 or UX-1) the value is garbage, exactly in the garbage zone of the
+            // tile edge. Lanes 0 / 31 have no such lane: unless they sit on a tile edge themselves
+            // (EDGE_FREE) they patch the value with a one-lane predicated load, no branch.
+            if (MG_STREAM_SHFL) {
+                q.l0 = __shfl_up_sync(0xffffffffu, q.c0[VX - 1], 1); q.l1 = __shfl_up_sync(0xffffffffu, q.c1[VX - 1], 1);
+                q.r0 = __shfl_down_sync(0xffffffffu, q.c0[0], 1); q.r1 = __shfl_down_sync(0xffffffffu, q.c1[0], 1);
+                if (!C::EDGE_FREE) {
+                    q.l0 = lds_if(lane == 0, aL + ib, q.l0); q.l1 = lds_if(lane == 0, aL + ib + ROWB, q.l1);
+                    q.r0 = lds_if(lane == 31, aR + ib, q.r0); q.r1 = lds_if(lane == 31, aR + ib + ROWB, q.r1);
+                }
+            } else {
+                q.l0 = lds1(aL + ib, (R)0); q.l1 = lds1(aL + ib + ROWB, (R)0);
+                q.r0 = lds1(aR + ib, (R)0); q.r1 = lds1(aR + ib + ROWB, (R)0);
+            }
+        };
+        // what a Jacobi stage does with its new plane o[]: masks, carry + ring for the next stage, or (last
+        // sweep) the global store, plus the neighbours' ghost planes
+        auto emit_jacobi = [&](int sidx, const A *o) {
+            const int s = sidx + 1, p = stage_p(sidx);
+            const bool pin = ST ? true : (p >= zdom0 && p < zdom1);
+            R outv[NP];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const bool keep = MK ? (((i < VX) ? in0 : in1) && pin) : pin;
+                outv[i] = (ST && !MK) ? (R)o[i] : (keep ? (R)o[i] : (R)0);
+            }
+            if (s < NST) {  // feed the next stage: own rows in registers, for the neighbours in the ring
+                if (CARRY) {
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) carry[sidx < NST - 1 ? sidx : 0][i] = outv[i];
+                }
+                if (worker) {
+                    const uint32_t ob = RING0 + (uint32_t)(2 * sidx + (t & 1)) * SB;
+                    Vec<R>::sts(a0 + ob, outv);
+                    Vec<R>::sts(a0 + ob + ROWB, outv + VX);
+                }
+            }
+            if (s == S && (ST || (p >= z0 && p < z1))) {
+                R *d = dcur;                                   // = dst0 + sLL * p (running pointer)
+                if (stm & 1) *(VT *)d = Vec<R>::pack(outv);
+                if (stm & 2) *(VT *)(d + sL) = Vec<R>::pack(outv + VX);
+                // boundary planes also land in the neighbours' ghost planes (peer stores)
+                if (has_peer) {
+                    const int nown = a.nz_hi - a.nz_lo;
+                    if (a.peer_lo != nullptr && p - a.nz_lo < a.ghost) {       // -> lower rank's upper ghost
+                        R *pd = a.peer_lo + (d - a.dst) + sLL * (size_t)nown;
+                        if (stm & 1) *(VT *)pd = Vec<R>::pack(outv);
+                        if (stm & 2) *(VT *)(pd + sL) = Vec<R>::pack(outv + VX);
+                    }
+                    if (a.peer_hi != nullptr && a.nz_hi - p <= a.ghost) {      // -> upper rank's lower ghost
+                        R *pd = a.peer_hi + (d - a.dst) - sLL * (size_t)nown;
+                        if (stm & 1) *(VT *)pd = Vec<R>::pack(outv);
+                        if (stm & 2) *(VT *)(pd + sL) = Vec<R>::pack(outv + VX);
+                    }
+                }
+            }
+        };
+        // the residual stage's plane o[]: rounded to storage like the reference's rs[L], then restricted;
+        // children in the order i fastest, then j, then k (SURVEY 8(a'))
+        auto emit_res = [&](const A *o) {
+            const int p = stage_p(NST - 1);
+            const bool pin = ST ? true : (p >= zdom0 && p < zdom1);
+            R outv[NP];
+#pragma unroll
+            for (int i = 0; i < NP; ++i) {
+                const bool keep = MK ? (((i < VX) ? in0 : in1) && pin) : pin;
+                outv[i] = (ST && !MK) ? (R)o[i] : (keep ? (R)o[i] : (R)0);
+            }
+            if (!((ST || (p >= z0 && p < z1)) && stm == 3)) return;
+            const int L2 = L >> 1;
+            if (((p - a.nz_lo) & 1) == 0) {
+#pragma unroll
+                for (int cidx = 0; cidx < VX / 2; ++cidx) {
+                    A sacc = Ar<A>::add((A)outv[2 * cidx], (A)outv[2 * cidx + 1]);
+                    sacc = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx]);
+                    rpart[cidx] = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx + 1]);
+                }
+            } else {
+                // coarse row of this unit in the coarse plane ((p - nz_lo) >> 1) + rz_off: a running
+                // offset, one coarse plane further after every store (chunks start on plane pairs)
+                const size_t cb = rcur;
+                rcur += (size_t)L2 * (size_t)L2;
+#pragma unroll
+                for (int cidx = 0; cidx < VX / 2; ++cidx) {
+                    A sacc = Ar<A>::add(rpart[cidx], (A)outv[2 * cidx]);
+                    sacc = Ar<A>::add(sacc, (A)outv[2 * cidx + 1]);
+                    sacc = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx]);
+                    sacc = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx + 1]);
+                    const R rv = (R)Ar<A>::mul((A).125, sacc);
+                    a.Rout[cb + cidx] = rv;
+                    const int qc = (p - a.nz_lo) >> 1, nc = (a.nz_hi - a.nz_lo) >> 1;   // coarse owned index / count
+                    if (a.rpeer_lo != nullptr && qc < a.ghost) a.rpeer_lo[cb + cidx + (size_t)L2 * L2 * (size_t)nc] = rv;
+                    if (a.rpeer_hi != nullptr && qc >= nc - a.ghost) a.rpeer_hi[cb + cidx - (size_t)L2 * L2 * (size_t)nc] = rv;
+                }
+            }
+        };
 
-            A tot[NP], o[NP];
-            if constexpr (kPackedF32 && std::is_same<A, float>::value && std::is_same<R, float>::value) {
-                // Blackwell packed fp32 (FADD2 / FFMA2 / FMUL2): two IEEE-rn operations per issue
-                // slot, bit-identical to the scalar form. Points are paired along x inside a vector.
-                auto P = [](float a, float b) { return make_float2(a, b); };
+        if constexpr (kPackedF32 && std::is_same<A, float>::value && std::is_same<R, float>::value) {
+            // Blackwell packed fp32, one stage after the other (LAST STAGE FIRST), one guard per stage
+            auto P = [](float a, float b) { return make_float2(a, b); };
+            const float2 INV = P(cf.inv_h2, cf.inv_h2), NINV = P(-cf.inv_h2, -cf.inv_h2), AD = P(cf.adiag, cf.adiag);
+            const float2 NAD = P(cf.nadiag, cf.nadiag), Y = P(cf.yneg, cf.yneg), M1 = P(-1.f, -1.f);
+#pragma unroll
+            for (int srev = 0; srev < NST; ++srev) {
+                const int sidx = NST - 1 - srev;
+                if (!stage_active(sidx)) continue;
+                const bool emit = stage_emit(sidx);
+                const bool is_res = RES && sidx == NST - 1;
+                In q;
+                load_inputs(sidx, emit, q);
                 // xl + xr pairs operands one element apart, which would cost register moves to pair up:
                 // these four sums per row stay scalar and land directly in aligned pairs
                 float2 sxx[4];
-                sxx[0] = P(__fadd_rn(l0, c0[1]), __fadd_rn(c0[0], c0[2])); sxx[1] = P(__fadd_rn(c0[1], c0[3]), __fadd_rn(c0[2], r0));
-                sxx[2] = P(__fadd_rn(l1, c1[1]), __fadd_rn(c1[0], c1[2])); sxx[3] = P(__fadd_rn(c1[1], c1[3]), __fadd_rn(c1[2], r1));
-                const float2 C[4] = {P(c0[0], c0[1]), P(c0[2], c0[3]), P(c1[0], c1[1]), P(c1[2], c1[3])};
-                const float2 YL[4] = {P(up[0], up[1]), P(up[2], up[3]), C[0], C[1]};
-                const float2 YR[4] = {C[2], C[3], P(dn[0], dn[1]), P(dn[2], dn[3])};
-                const float2 INV = P(cf.inv_h2, cf.inv_h2), NINV = P(-cf.inv_h2, -cf.inv_h2), AD = P(cf.adiag, cf.adiag);
-                const float2 NAD = P(cf.nadiag, cf.nadiag), Y = P(cf.yneg, cf.yneg), M1 = P(-1.f, -1.f);
+                sxx[0] = P(__fadd_rn(q.l0, q.c0[1]), __fadd_rn(q.c0[0], q.c0[2])); sxx[1] = P(__fadd_rn(q.c0[1], q.c0[3]), __fadd_rn(q.c0[2], q.r0));
+                sxx[2] = P(__fadd_rn(q.l1, q.c1[1]), __fadd_rn(q.c1[0], q.c1[2])); sxx[3] = P(__fadd_rn(q.c1[1], q.c1[3]), __fadd_rn(q.c1[2], q.r1));
+                const float2 Cc[4] = {P(q.c0[0], q.c0[1]), P(q.c0[2], q.c0[3]), P(q.c1[0], q.c1[1]), P(q.c1[2], q.c1[3])};
+                const float2 YL[4] = {P(q.up[0], q.up[1]), P(q.up[2], q.up[3]), Cc[0], Cc[1]};
+                const float2 YR[4] = {Cc[2], Cc[3], P(q.dn[0], q.dn[1]), P(q.dn[2], q.dn[3])};
                 float2 T[4], F[4];
+                float o[NP];
 #pragma unroll
                 for (int k = 0; k < 4; ++k) {
                     const float2 part = __fadd2_rn(__fadd2_rn(sxx[k], YL[k]), YR[k]);
                     const float2 PRV = P(prev[sidx][2 * k], prev[sidx][2 * k + 1]);
-                    T[k] = __fadd2_rn(P(acc[sidx][2 * k], acc[sidx][2 * k + 1]), C[k]);   // pending plane gets its z+1
-                    F[k] = P(fv[2 * k], fv[2 * k + 1]);
+                    T[k] = __fadd2_rn(P(acc[sidx][2 * k], acc[sidx][2 * k + 1]), Cc[k]);   // pending plane gets its z+1
+                    F[k] = P(q.fv[2 * k], q.fv[2 * k + 1]);
                     if (is_res) {
                         const float2 au = __fadd2_rn(__fmul2_rn(T[k], INV), __fmul2_rn(AD, PRV));
                         const float2 rv = __ffma2_rn(au, M1, F[k]);                        // f - au
@@ -460,121 +607,79 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                     }
                     const float2 NA = __fadd2_rn(part, PRV);                               // this plane gets its z-1
                     acc[sidx][2 * k] = NA.x; acc[sidx][2 * k + 1] = NA.y;
-                    prev[sidx][2 * k] = C[k].x; prev[sidx][2 * k + 1] = C[k].y;
-                    tot[2 * k] = T[k].x; tot[2 * k + 1] = T[k].y;
+                    prev[sidx][2 * k] = Cc[k].x; prev[sidx][2 * k + 1] = Cc[k].y;
                 }
                 if (!emit) continue;
-                if (!is_res) {
-                    float2 N[4];
-                    unsigned int m = 0xffffffffu;
+                if (is_res) { emit_res(o); continue; }
+                float2 N[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k) N[k] = __ffma2_rn(T[k], NINV, F[k]);           // RN(f - S/h^2)
+                // Division guard (mg_math.cuh): the Markstein sequence is exact unless a numerator is tiny
+                // but non-zero; one integer min-chain per group (the key ranks exact zeros highest), IEEE
+                // division for the group otherwise. (A floating-point pre-test of min |n| with FMNMX3 was
+                // measured 10 % slower per V-cycle.)
+                unsigned int m = 0xffffffffu;
+#pragma unroll
+                for (int k = 0; k < 4; ++k) m = min(m, min(Ar<float>::guard_key(N[k].x), Ar<float>::guard_key(N[k].y)));
+                if (m >= Ar<float>::guard_threshold()) {
 #pragma unroll
                     for (int k = 0; k < 4; ++k) {
-                        N[k] = __ffma2_rn(T[k], NINV, F[k]);                               // RN(f - S/h^2)
-                        const unsigned int ka = Ar<float>::guard_key(N[k].x), kb = Ar<float>::guard_key(N[k].y);
-                        m = min(m, min(ka, kb));
-                    }
-                    if (m >= Ar<float>::guard_threshold()) {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            const float2 q1 = __fmul2_rn(N[k], Y);
-                            const float2 rr = __ffma2_rn(NAD, q1, N[k]);
-                            const float2 q2 = __ffma2_rn(rr, Y, q1);
-                            o[2 * k] = q2.x; o[2 * k + 1] = q2.y;
-                        }
-                    } else {
-#pragma unroll
-                        for (int k = 0; k < 4; ++k) {
-                            o[2 * k] = Ar<float>::div(N[k].x, cf.adiag);
-                            o[2 * k + 1] = Ar<float>::div(N[k].y, cf.adiag);
-                        }
-                    }
-                }
-            } else {
-#pragma unroll
-            for (int i = 0; i < VX; ++i) {
-                {   // row 0 of the unit
-                    const A xl = (A)(i == 0 ? l0 : c0[i - 1]), xr = (A)(i == VX - 1 ? r0 : c0[i + 1]);
-                    const A yl = (A)up[i], yr = (A)c1[i], c = (A)c0[i];
-                    const A part = Ar<A>::add(Ar<A>::add(Ar<A>::add(xl, xr), yl), yr);
-                    tot[i] = Ar<A>::add(acc[sidx][i], c);                      // pending plane gets its z+1
-                    if (is_res) o[i] = residual_point<A>(tot[i], (A)fv[i], prev[sidx][i], cf);
-                    acc[sidx][i] = Ar<A>::add(part, prev[sidx][i]);            // this plane gets its z-1
-                    prev[sidx][i] = c;
-                }
-                {   // row 1 of the unit
-                    const int j = VX + i;
-                    const A xl = (A)(i == 0 ? l1 : c1[i - 1]), xr = (A)(i == VX - 1 ? r1 : c1[i + 1]);
-                    const A yl = (A)c0[i], yr = (A)dn[i], c = (A)c1[i];
-                    const A part = Ar<A>::add(Ar<A>::add(Ar<A>::add(xl, xr), yl), yr);
-                    tot[j] = Ar<A>::add(acc[sidx][j], c);
-                    if (is_res) o[j] = residual_point<A>(tot[j], (A)fv[j], prev[sidx][j], cf);
-                    acc[sidx][j] = Ar<A>::add(part, prev[sidx][j]);
-                    prev[sidx][j] = c;
-                }
-            }
-            if (!emit) continue;
-            if (!is_res) {
-                A num[NP];
-#pragma unroll
-                for (int i = 0; i < NP; ++i) num[i] = jacobi_num<A>(tot[i], (A)fv[i], cf);
-                div_adiag_group<3, A, NP>(num, o, cf);
-            }
-            }
-            R outv[NP];
-#pragma unroll
-            for (int i = 0; i < NP; ++i) {
-                const bool keep = MK ? (((i < VX) ? in0 : in1) && pin) : pin;
-                outv[i] = (ST && !MK) ? (R)o[i] : (keep ? (R)o[i] : (R)0);
-            }
-
-            if (!is_res) {
-                if (s < NST && worker) {  // feed the next stage
-                    R *out = ring_slot(sidx, t & 1);
-                    *(VT *)(out + off0) = Vec<R>::pack(outv);
-                    *(VT *)(out + off1) = Vec<R>::pack(outv + VX);
-                }
-                if (last_jacobi && (ST || (p >= z0 && p < z1))) {
-                    R *d = dst0 + sLL * (size_t)p;
-                    if (st0) *(VT *)d = Vec<R>::pack(outv);
-                    if (st1) *(VT *)(d + sL) = Vec<R>::pack(outv + VX);
-                    // boundary planes also land in the neighbours' ghost planes (peer stores)
-                    const int nown = a.nz_hi - a.nz_lo;
-                    if (a.peer_lo != nullptr && p - a.nz_lo < a.ghost) {       // -> lower rank's upper ghost
-                        R *pd = a.peer_lo + (dst0 - a.dst) + sLL * (size_t)(p + nown);
-                        if (st0) *(VT *)pd = Vec<R>::pack(outv);
-                        if (st1) *(VT *)(pd + sL) = Vec<R>::pack(outv + VX);
-                    }
-                    if (a.peer_hi != nullptr && a.nz_hi - p <= a.ghost) {      // -> upper rank's lower ghost
-                        R *pd = a.peer_hi + (dst0 - a.dst) + sLL * (size_t)(p - nown);
-                        if (st0) *(VT *)pd = Vec<R>::pack(outv);
-                        if (st1) *(VT *)(pd + sL) = Vec<R>::pack(outv + VX);
-                    }
-                }
-            } else if ((ST || (p >= z0 && p < z1)) && st0 && st1) {
-                // restriction: children in the order i fastest, then j, then k (SURVEY 8(a'))
-                const int L2 = L >> 1;
-                if (((p - a.nz_lo) & 1) == 0) {
-#pragma unroll
-                    for (int cidx = 0; cidx < VX / 2; ++cidx) {
-                        A sacc = Ar<A>::add((A)outv[2 * cidx], (A)outv[2 * cidx + 1]);
-                        sacc = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx]);
-                        rpart[cidx] = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx + 1]);
+                        const float2 q1 = __fmul2_rn(N[k], Y);
+                        const float2 rr = __ffma2_rn(NAD, q1, N[k]);
+                        const float2 q2 = __ffma2_rn(rr, Y, q1);
+                        o[2 * k] = q2.x; o[2 * k + 1] = q2.y;
                     }
                 } else {
-                    const size_t cb = (size_t)(gx0 >> 1) +
-                                      (size_t)L2 * ((size_t)(gy0 >> 1) + (size_t)L2 * (size_t)(((p - a.nz_lo) >> 1) + a.rz_off));
 #pragma unroll
-                    for (int cidx = 0; cidx < VX / 2; ++cidx) {
-                        A sacc = Ar<A>::add(rpart[cidx], (A)outv[2 * cidx]);
-                        sacc = Ar<A>::add(sacc, (A)outv[2 * cidx + 1]);
-                        sacc = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx]);
-                        sacc = Ar<A>::add(sacc, (A)outv[VX + 2 * cidx + 1]);
-                        const R rv = (R)Ar<A>::mul((A).125, sacc);
-                        a.Rout[cb + cidx] = rv;
-                        const int qc = (p - a.nz_lo) >> 1, nc = (a.nz_hi - a.nz_lo) >> 1;   // coarse owned index / count
-                        if (a.rpeer_lo != nullptr && qc < a.ghost) a.rpeer_lo[cb + cidx + (size_t)L2 * L2 * (size_t)nc] = rv;
-                        if (a.rpeer_hi != nullptr && qc >= nc - a.ghost) a.rpeer_hi[cb + cidx - (size_t)L2 * L2 * (size_t)nc] = rv;
+                    for (int k = 0; k < 4; ++k) {
+                        o[2 * k] = Ar<float>::div(N[k].x, cf.adiag);
+                        o[2 * k + 1] = Ar<float>::div(N[k].y, cf.adiag);
                     }
+                }
+                emit_jacobi(sidx, o);
+            }
+        } else {
+            // generic arithmetic (8-byte accumulators): one stage after the other, LAST STAGE FIRST
+#pragma unroll
+            for (int srev = 0; srev < NST; ++srev) {
+                const int sidx = NST - 1 - srev;
+                if (!stage_active(sidx)) continue;
+                const bool emit = stage_emit(sidx);
+                const bool is_res = RES && sidx == NST - 1;
+                In q;
+                load_inputs(sidx, emit, q);
+                A tot[NP], o[NP];
+#pragma unroll
+                for (int i = 0; i < VX; ++i) {
+                    {   // row 0 of the unit
+                        const A xl = (A)(i == 0 ? q.l0 : q.c0[i - 1]), xr = (A)(i == VX - 1 ? q.r0 : q.c0[i + 1]);
+                        const A yl = (A)q.up[i], yr = (A)q.c1[i], c = (A)q.c0[i];
+                        const A part = Ar<A>::add(Ar<A>::add(Ar<A>::add(xl, xr), yl), yr);
+                        tot[i] = Ar<A>::add(acc[sidx][i], c);                      // pending plane gets its z+1
+                        if (is_res) o[i] = residual_point<A>(tot[i], (A)q.fv[i], prev[sidx][i], cf);
+                        acc[sidx][i] = Ar<A>::add(part, prev[sidx][i]);            // this plane gets its z-1
+                        prev[sidx][i] = c;
+                    }
+                    {   // row 1 of the unit
+                        const int j = VX + i;
+                        const A xl = (A)(i == 0 ? q.l1 : q.c1[i - 1]), xr = (A)(i == VX - 1 ? q.r1 : q.c1[i + 1]);
+                        const A yl = (A)q.c0[i], yr = (A)q.dn[i], c = (A)q.c1[i];
+                        const A part = Ar<A>::add(Ar<A>::add(Ar<A>::add(xl, xr), yl), yr);
+                        tot[j] = Ar<A>::add(acc[sidx][j], c);
+                        if (is_res) o[j] = residual_point<A>(tot[j], (A)q.fv[j], prev[sidx][j], cf);
+                        acc[sidx][j] = Ar<A>::add(part, prev[sidx][j]);
+                        prev[sidx][j] = c;
+                    }
+                }
+                if (!emit) continue;
+                if (is_res) {
+                    emit_res(o);
+                } else {
+                    A num[NP];
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) num[i] = jacobi_num<A>(tot[i], (A)q.fv[i], cf);
+                    div_adiag_group<3, A, NP>(num, o, cf);
+                    emit_jacobi(sidx, o);
                 }
             }
         }
@@ -582,18 +687,16 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         // (PRO) prepare next step's source plane in place
         if (PRO && t + 1 < nin) {
             const int sn = su + 1 == NSLOT ? 0 : su + 1;
-            mbar_wait(&mbar_u[sn], (uint32_t)(sn == 0 ? pu ^ 1 : pu));
-            fix_apply(sn);
+            mbar_wait(mb_u + 8 * sn, (uint32_t)(sn == 0 ? pu ^ 1 : pu));
+            fix_apply((uint32_t)sn * SB);
         }
         __syncthreads();
         // advance the ring cursors
-        if (++su == NSLOT) { su = 0; pu ^= 1; }
-        if (++sf == NF) { sf = 0; pf ^= 1; }
+        bu += SB; bfq += SB;
+        dcur += sLL;
+        if (++su == NSLOT) { su = 0; bu = 0; pu ^= 1; }
+        if (++sf == NF) { sf = 0; bfq = 0; }
     };
-
-    // f plane 0 is fetched only to keep the ring's mbarrier phases uniform; it must still have
-    // landed before this CTA may exit (no TMA transfer may outlive its shared memory)
-    mbar_wait(&mbar_f[0], 0);
 
     // Steady range: all stages active and emitting, every emitted plane inside the grid. The
     // three phases (fill, steady, drain) are separate loops so that the per-stage registers
