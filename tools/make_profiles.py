@@ -108,7 +108,7 @@ def main():
             "Commands (on a B200, each right after the same command exited 0 without ncu):", "", "```",
             "ncu --set full --clock-control none --import-source on -k regex:k_stream3d -s 0 -c 12 -o prof \\",
             "    python bench.py --steps 3 --warmup 3 --no-cpu", "```", "",
-            "3-D 512^3 fp32, default tuning: tb = 4 (pre = [4][3+RES], post = [PRO+4][3]), tile 88 x 24 (+halo 96 x 32),",
+            "3-D 512^3 fp32, default tuning: tb = 4 (pre = [4][3+RES], post = [PRO+4][3]), tile 56 x 40 (+halo 64 x 48),",
             "balanced persistent partition (one CTA per SM), f ring via TMA, packed fp32 arithmetic. The twelve launches are the",
             "streaming-smoother passes of one V-cycle (L = 512, 256, 128). A_op = algorithmic bytes of the reference operators a",
             "launch replaces (SURVEY 8(d)); DRAM = dram__bytes_read.sum + dram__bytes_write.sum of that launch.",
