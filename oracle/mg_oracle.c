@@ -10,12 +10,19 @@
  *
  * PARITY PINNING. The reference ships no golden vectors, no assertions and no fixtures
  * (SURVEY.md section 4), no Lua runtime exists in this image, and the reference is not
- * C/C++/Python, so neither `oracle/_ref` nor imported-Python fixtures are possible. This
- * oracle is pinned by the hand-derived known answers KA1-KA5 of SURVEY.md section 8(c)
- * (tests/test_oracle_known_answers.py) and by committed fixtures generated from this file
- * (tests/golden/, script tests/golden/make_golden.py). With respect to reference-run
- * outputs the status is therefore: **parity unpinned by reference artefacts** (2-D), and
- * the 3-D rules are this project's own extension (SURVEY.md section 8(a')).
+ * C/C++/Python, so neither `oracle/_ref` nor imported-Python fixtures are possible. Instead the
+ * reference's OWN SOURCE TEXT (cpu-raw.lua, unmodified) is executed by a purpose-built Lua
+ * interpreter (oracle/minilua.py, driver oracle/run_reference.py) and what it computes in run()
+ * -- both err values, f, psi, psiOld, rs/Rs/vs/Vs of every level and the complete sequence of
+ * `show` dumps of twoGrid -- is committed as tests/golden/ref_2d_*.npz (sizes 2..64, real =
+ * double and float). tests/test_reference_source.py requires this oracle to reproduce those
+ * fixtures BIT FOR BIT; tests/test_gpu_vcycle.py requires the same of the CUDA path. Status:
+ * 2-D f64 and f32-storage modes PINNED TO THE REFERENCE SOURCE AS EXECUTED BY minilua (not by
+ * LuaJIT itself: see the fidelity argument in minilua.py); the fp32-arithmetic mode (gpu.lua on
+ * an fp32 device) and the 3-D rules (this project's extension, SURVEY.md section 8(a')) have no
+ * reference run to be pinned to. The hand-derived known answers KA1-KA5 of SURVEY.md section
+ * 8(c) (tests/test_oracle_known_answers.py) and the oracle-generated fixtures
+ * (tests/golden/make_golden.py) remain as independent checks.
  *
  * Reference functions restated (file:line in /root/reference):
  *   initCells        cpu-raw.lua:8-20        -> orc_init_cells

@@ -1,6 +1,7 @@
 """pytest configuration: `gpu` marker, path-based import of the product package.
 
--m "not gpu": oracle vs known answers / golden fixtures, host logic, C-ABI load + symbols.
+-m "not gpu": oracle vs the reference-source run (tests/golden/ref_*), known answers, golden fixtures, host logic,
+              C-ABI load + symbols.
 -m gpu      : parity tests proper -- CUDA path through the C ABI vs the CPU oracle.
 """
 import importlib.util

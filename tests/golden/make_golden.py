@@ -1,10 +1,11 @@
 """Generates tests/golden/*.npz from the CPU oracle (oracle/mg_oracle.c).
 
-The reference ships no golden vectors and cannot be executed in this image (no Lua runtime),
-so these fixtures do not pin the oracle to the reference; they pin the oracle to ITSELF at
-the commit that generated them, so that later edits to the oracle cannot silently change the
-numbers the CUDA path is compared against. The oracle's tie to the reference is the
-hand-derived known answers in tests/test_oracle_known_answers.py.
+These fixtures pin the oracle to ITSELF at the commit that generated them (including the 3-D
+cases and cycle counts the reference never runs), so that later edits to the oracle cannot
+silently change the numbers the CUDA path is compared against. The oracle's tie to the
+REFERENCE is separate: tests/golden/ref_2d_*.npz, produced by executing the reference's own
+cpu-raw.lua (oracle/run_reference.py), and the hand-derived known answers in
+tests/test_oracle_known_answers.py.
 
 Run:  python tests/golden/make_golden.py
 """

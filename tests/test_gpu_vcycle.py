@@ -80,7 +80,33 @@ def test_random_rhs_and_guess(mgp, orc, dim, size, real):
     s.close()
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "*.npz"))),
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "ref_2d_*.npz"))),
+                         ids=lambda p: os.path.basename(p)[:-4])
+def test_cuda_matches_the_reference_source_run(mgp, path):
+    """tests/golden/ref_2d_*.npz = what the reference's own cpu-raw.lua computes in run() (2 V-cycles) when executed by
+    oracle/minilua.py (oracle/run_reference.py). The CUDA path, through the C ABI, must give the same bits."""
+    g = np.load(path)
+    dim, size, kind, cycles = (int(x) for x in g["meta"])
+    s = mgp.MultigridCUDA(size, kind, dim=dim, out=False)
+    assert_bits_equal(s.f.download().ravel(), g["f0"], "f after init")
+    assert_bits_equal(s.psi.download().ravel(), g["psi0"], "psi after init")
+    for c in range(cycles):
+        e = s.step()
+        assert abs(e - g["errs"][c]) <= err_rtol(size ** dim) * g["errs"][c]
+        if c == 0:
+            assert_bits_equal(s.psi.download().ravel(), g["psi_after_cycle1"], "psi after cycle 1")
+    assert_bits_equal(s.psi.download().ravel(), g["psi"], "psi after run()")
+    assert_bits_equal(s.psiOld.download().ravel(), g["psiOld"], "psiOld after run()")
+    L = size // 2
+    while L >= 1:
+        assert_bits_equal(s.Rs[L].download().ravel(), g[f"Rs{L}"], f"Rs[{L}]")
+        assert_bits_equal(s.Vs[L].download().ravel(), g[f"Vs{L}"], f"Vs[{L}]")
+        L //= 2
+    s.close()
+
+
+@pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz"))
+                                        if not os.path.basename(p).startswith("ref_")),
                          ids=lambda p: os.path.basename(p)[:-4])
 def test_cuda_matches_golden_fixtures(mgp, path):
     g = np.load(path)
