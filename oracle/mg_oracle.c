@@ -15,13 +15,17 @@
  * interpreter (oracle/minilua.py, driver oracle/run_reference.py) and what it computes in run()
  * -- both err values, f, psi, psiOld, rs/Rs/vs/Vs of every level and the complete sequence of
  * `show` dumps of twoGrid -- is committed as tests/golden/ref_2d_*.npz (sizes 2..64, real =
- * double and float). tests/test_reference_source.py requires this oracle to reproduce those
- * fixtures BIT FOR BIT; tests/test_gpu_vcycle.py requires the same of the CUDA path. Status:
- * 2-D f64 and f32-storage modes PINNED TO THE REFERENCE SOURCE AS EXECUTED BY minilua (not by
- * LuaJIT itself: see the fidelity argument in minilua.py); the fp32-arithmetic mode (gpu.lua on
- * an fp32 device) and the 3-D rules (this project's extension, SURVEY.md section 8(a')) have no
- * reference run to be pinned to. The hand-derived known answers KA1-KA5 of SURVEY.md section
- * 8(c) (tests/test_oracle_known_answers.py) and the oracle-generated fixtures
+ * double and float). The same is done for gpu.lua (oracle/run_reference_gpu.py): its host code
+ * runs under minilua on a fake in-memory OpenCL device whose kernels are gpu.lua's own OpenCL C
+ * source compiled by gcc (-ffp-contract=off) into oracle/_ref/ -> tests/golden/refgpu_2d_*.npz
+ * (real = float there is fp32 ARITHMETIC). tests/test_reference_source.py requires this oracle
+ * to reproduce all those fixtures BIT FOR BIT; tests/test_gpu_vcycle.py requires the same of the
+ * CUDA path. Status: the three 2-D modes (f64, f32 storage + f64 arithmetic, f32) are PINNED TO
+ * THE REFERENCE SOURCE AS EXECUTED BY minilua (+ gcc for the kernels) -- not by LuaJIT / an
+ * OpenCL device: see the fidelity arguments in minilua.py and run_reference_gpu.py. The 3-D rules
+ * are this project's extension (SURVEY.md section 8(a')) and have no reference run to be pinned
+ * to. The hand-derived known answers KA1-KA5 of SURVEY.md section 8(c)
+ * (tests/test_oracle_known_answers.py) and the oracle-generated fixtures
  * (tests/golden/make_golden.py) remain as independent checks.
  *
  * Reference functions restated (file:line in /root/reference):

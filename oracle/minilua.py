@@ -119,7 +119,7 @@ def lua_index(obj, k):
     if hasattr(obj, "lua_index"):
         return obj.lua_index(k)
     if isinstance(obj, str):
-        raise LuaError("string indexing is not supported by minilua")
+        return STRING_LIB.get(k)     # s:method(...) resolves through the string library, as in Lua
     raise LuaError(f"attempt to index a {type(obj).__name__} value with key {k!r}")
 
 
@@ -159,6 +159,110 @@ def lua_call(f, args):
             return list(r)
         return [r]
     raise LuaError(f"attempt to call a {type(f).__name__} value")
+
+
+# ----------------------------------------------------------------------------- string library (the few functions used)
+_LUA_CLASS = {"a": "A-Za-z", "d": "0-9", "l": "a-z", "u": "A-Z", "w": "A-Za-z0-9", "s": r" \t\n\r\f\v", "x": "0-9A-Fa-f",
+              "p": r"!-/:-@\[-`{-~"}
+
+
+def lua_pattern_to_regex(pat):
+    """Translates the common part of Lua patterns (%a %d %l %u %w %s %x %p and their complements, sets, anchors,
+    * + - ?, captures, %-escapes) to a Python regular expression. %b and %f are not supported."""
+    out, i, n = [], 0, len(pat)
+
+    def cls(c, in_set):
+        lo = c.lower()
+        if lo in _LUA_CLASS:
+            body = _LUA_CLASS[lo]
+            if c.isupper():
+                if in_set:
+                    raise LuaError("complemented class inside a set is not supported by minilua")
+                return "[^" + body + "]"
+            return body if in_set else "[" + body + "]"
+        return re.escape(c)
+
+    while i < n:
+        c = pat[i]
+        if c == "%":
+            i += 1
+            if i >= n:
+                raise LuaError("malformed pattern (ends with '%')")
+            if pat[i] in "bf":
+                raise LuaError("%b / %f patterns are not supported by minilua")
+            out.append(cls(pat[i], False))
+        elif c == "[":
+            j = i + 1
+            body = "["
+            if j < n and pat[j] == "^":
+                body += "^"
+                j += 1
+            first = True
+            while j < n and (pat[j] != "]" or first):
+                first = False
+                if pat[j] == "%":
+                    j += 1
+                    body += cls(pat[j], True)
+                else:
+                    body += "\\" + pat[j] if pat[j] in "\\[]" else pat[j]
+                j += 1
+            out.append(body + "]")
+            i = j
+        elif c == "-":
+            out.append("*?")
+        elif c in "*+?()":
+            out.append(c)
+        elif c == "^" and i == 0:
+            out.append("^")
+        elif c == "$" and i == n - 1:
+            out.append("$")
+        elif c == ".":
+            out.append("(?s:.)")
+        else:
+            out.append(re.escape(c))
+        i += 1
+    return "".join(out)
+
+
+def _str_match(s, pat, init=1):
+    m = re.compile(lua_pattern_to_regex(pat)).search(s, int(init) - 1)
+    if m is None:
+        return (None,)
+    return tuple(m.groups()) if m.groups() else (m.group(0),)
+
+
+def _str_find(s, pat, init=1, plain=None):
+    if lua_truth(plain):
+        i = s.find(pat, int(init) - 1)
+        return (None,) if i < 0 else (float(i + 1), float(i + len(pat)))
+    m = re.compile(lua_pattern_to_regex(pat)).search(s, int(init) - 1)
+    if m is None:
+        return (None,)
+    return (float(m.start() + 1), float(m.end())) + tuple(m.groups())
+
+
+def _str_format(fmt, *args):
+    return fmt % tuple(int(a) if isinstance(a, float) and a.is_integer() and re.search(r"%[-+ #0]*\d*d", fmt) else a for a in args)
+
+
+class _StringLib:
+    def __init__(self):
+        self.fns = {"lower": lambda s, *_: s.lower(), "upper": lambda s, *_: s.upper(), "len": lambda s: float(len(s)),
+                    "sub": lambda s, i=1, j=-1: s[(int(i) - 1 if i > 0 else max(len(s) + int(i), 0)):(int(j) if j >= 0 else len(s) + int(j) + 1)],
+                    "rep": lambda s, n: s * int(n), "match": _str_match, "find": _str_find, "format": _str_format,
+                    "byte": lambda s, i=1: float(ord(s[int(i) - 1])), "char": lambda *a: "".join(chr(int(x)) for x in a)}
+
+    def get(self, k):
+        return self.fns.get(k)
+
+    def as_table(self):
+        t = LuaTable()
+        for k, v in self.fns.items():
+            t.set(k, v)
+        return t
+
+
+STRING_LIB = _StringLib()
 
 
 # ----------------------------------------------------------------------------- lexer
@@ -1012,6 +1116,10 @@ class Interpreter:
         io = LuaTable()
         io.set("write", self._io_write)
         g["io"] = io
+        g["string"] = STRING_LIB.as_table()
+        # LuaJIT loads its `bit` library as a global as well (gpu.lua:257 uses it without a require)
+        g["bit"] = self.table_from({"lshift": lambda a, n: float(int(a) << int(n)), "rshift": lambda a, n: float(int(a) >> int(n)),
+                                    "band": lambda a, b: float(int(a) & int(b)), "bor": lambda a, b: float(int(a) | int(b))})
         g["_G"] = None
 
     # --- helpers for embedding
@@ -1035,6 +1143,7 @@ class Interpreter:
                 return r
             return math.log2(x) if base == 2 else (math.log10(x) if base == 10 else r / math.log(base))
         return {"floor": lambda x: float(math.floor(x)), "ceil": lambda x: float(math.ceil(x)),
+                "tointeger": lambda x: float(int(x)),
                 "sqrt": lambda x: math.sqrt(x) if x >= 0 else math.nan, "abs": lambda x: abs(x), "huge": math.inf, "pi": math.pi,
                 "log": log, "exp": math.exp, "sin": math.sin, "cos": math.cos,
                 "max": lambda *a: max(a), "min": lambda *a: min(a), "pow": _lua_pow, "fmod": math.fmod}

@@ -80,11 +80,14 @@ def test_random_rhs_and_guess(mgp, orc, dim, size, real):
     s.close()
 
 
-@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "ref_2d_*.npz"))),
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "ref_2d_*.npz")) +
+                                        glob.glob(os.path.join(HERE, "golden", "refgpu_2d_*.npz"))),
                          ids=lambda p: os.path.basename(p)[:-4])
 def test_cuda_matches_the_reference_source_run(mgp, path):
     """tests/golden/ref_2d_*.npz = what the reference's own cpu-raw.lua computes in run() (2 V-cycles) when executed by
-    oracle/minilua.py (oracle/run_reference.py). The CUDA path, through the C ABI, must give the same bits."""
+    oracle/minilua.py (oracle/run_reference.py); refgpu_2d_*.npz = the same for gpu.lua with its own OpenCL kernel
+    source compiled strictly by gcc (oracle/run_reference_gpu.py; real = float there is fp32 arithmetic, MG_REAL_F32).
+    The CUDA path, through the C ABI, must give the same bits."""
     g = np.load(path)
     dim, size, kind, cycles = (int(x) for x in g["meta"])
     s = mgp.MultigridCUDA(size, kind, dim=dim, out=False)

@@ -12,6 +12,12 @@ oracle/minilua.py (generator: oracle/run_reference.py; there is no Lua runtime i
      reproduces the committed fixture.
 
 cpu-raw.lua's real = 'float' stores fp32 and computes in Lua numbers (doubles): the oracle's "float_acc64".
+
+`tests/golden/refgpu_2d_*.npz` are the same for `gpu.lua` (generator: oracle/run_reference_gpu.py): its Lua host code
+runs under minilua on a fake in-memory OpenCL device whose kernels are the reference's own OpenCL C source compiled by
+gcc with -ffp-contract=off. real = 'float' there means fp32 storage AND fp32 arithmetic: the oracle's "float", the
+arithmetic of the headline benchmark. gpu.lua never dumps the top-level f before the pre-smoothing sweeps (its test
+`L==size` reads an undefined global, gpu.lua:268), so those seven dumps per cycle are dropped from the oracle's trace.
 """
 import glob
 import io
@@ -28,7 +34,7 @@ import oracle as O  # noqa: E402
 import minilua as ml  # noqa: E402
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
-FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "ref_2d_*.npz")))
+FIXTURES = sorted(glob.glob(os.path.join(GOLDEN, "ref_2d_*.npz"))) + sorted(glob.glob(os.path.join(GOLDEN, "refgpu_2d_*.npz")))
 
 
 def _bits(a):
@@ -46,7 +52,8 @@ def _same(got, want, what):
 
 def test_fixtures_present():
     names = {os.path.basename(f) for f in FIXTURES}
-    assert {"ref_2d_64_f64.npz", "ref_2d_64_f32.npz", "ref_2d_32_f64.npz", "ref_2d_8_f64.npz", "ref_2d_2_f64.npz"} <= names
+    assert {"ref_2d_64_f64.npz", "ref_2d_64_f32.npz", "ref_2d_32_f64.npz", "ref_2d_8_f64.npz", "ref_2d_2_f64.npz",
+            "refgpu_2d_64_f32.npz", "refgpu_2d_128_f32.npz", "refgpu_2d_8_f32.npz", "refgpu_2d_32_f64.npz"} <= names
 
 
 @pytest.mark.parametrize("path", FIXTURES, ids=[os.path.basename(f)[:-4] for f in FIXTURES])
@@ -54,7 +61,8 @@ def test_oracle_equals_reference_source(path):
     g = np.load(path)
     dim, size, real_kind, cycles = (int(x) for x in g["meta"])
     assert dim == 2 and cycles == 2
-    real = {0: "double", 2: "float_acc64"}[real_kind]
+    real = {0: "double", 1: "float", 2: "float_acc64"}[real_kind]
+    from_gpu_lua = os.path.basename(path).startswith("refgpu_")
     o = O.Oracle(size, real, dim)
     _same(o.f, g["f0"], "f after init (initCells, cpu-raw.lua:8-20)")
     _same(o.psi, g["psi0"], "psi after init")
@@ -77,11 +85,31 @@ def test_oracle_equals_reference_source(path):
         L *= 2
     # the stage-by-stage dumps, in the reference's own order
     tr = o.trace()
+    if from_gpu_lua:   # drop the debugging-only dump of f before each of the 7 top-level pre-smoothing sweeps, per cycle
+        per = len(tr) // cycles
+        tr = [t for i, t in enumerate(tr) if not (i % per < 14 and i % per % 2 == 0)]
     assert [n for n, _, _ in tr] == [str(n) for n in g["trace_names"]], "sequence of dumped buffer names"
     assert [l for _, l, _ in tr] == [int(l) for l in g["trace_L"]], "sequence of dumped levels"
     if "t00000" in g.files:
         for i, (n, l, a) in enumerate(tr):
             _same(a, g[f"t{i:05d}"], f"dump #{i} ({n}, L = {l})")
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/gpu.lua"), reason="reference tree not present (GPU box)")
+@pytest.mark.parametrize("size,fp64", [(8, False), (8, True)])
+def test_rerunning_gpu_lua_reproduces_the_fixture(size, fp64):
+    import run_reference_gpu as rg
+    r = rg.run_reference_gpu(size, fp64)
+    assert r["real"] == ("double" if fp64 else "float")     # gpu.lua:32 picks real from the device's fp64 extension
+    g = np.load(os.path.join(GOLDEN, f"refgpu_2d_{size}_{'f64' if fp64 else 'f32'}.npz"))
+    assert [float(e) for e in g["errs"]] == [float(e) for e in r["errs"]]
+    _same(r["psi"], g["psi"], "psi")
+    # the kernel sequence of one twoGrid level visit (gpu.lua:296-346): 7 x Jacobi, calcResidual, reduceResidual, ...
+    names = [n for n, _ in r["launches"]]
+    assert names[0] == "init" and names[1:8] == ["Jacobi"] * 7 and names[8:10] == ["calcResidual", "reduceResidual"]
+    assert names.count("calcFrobErr") == 2 and names.count("expandResidual") == names.count("addTo") == 2 * 3
+    for i, (n, l, a) in enumerate(r["trace"]):
+        _same(a, g[f"t{i:05d}"], f"dump #{i}")
 
 
 @pytest.mark.skipif(not os.path.exists("/root/reference/cpu-raw.lua"), reason="reference tree not present (GPU box)")
