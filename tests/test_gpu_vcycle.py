@@ -109,7 +109,7 @@ def test_cuda_matches_the_reference_source_run(mgp, path):
 
 
 @pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz"))
-                                        if not os.path.basename(p).startswith("ref_")),
+                                        if not os.path.basename(p).startswith("ref")),
                          ids=lambda p: os.path.basename(p)[:-4])
 def test_cuda_matches_golden_fixtures(mgp, path):
     g = np.load(path)
