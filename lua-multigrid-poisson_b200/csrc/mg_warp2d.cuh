@@ -13,6 +13,11 @@
 // the y+1 neighbour completes the pending sum `acc` one step later. No shared memory, no
 // __syncthreads(), no intermediate field ever touches L2/HBM. The summation order
 // ((xl+xr)+yl)+yr of the reference is preserved => bit-identical to one sweep per launch.
+// fp32 arithmetic is issued as packed FADD2 / FFMA2 / FMUL2 (two IEEE-rn operations per issue slot); the
+// rows where every stage is active and inside the grid run a predicate-free body.
+// (MEASURED: making the stages of a step independent -- stage s+1 consuming what stage s emitted a
+// step earlier, as the 3-D kernel does -- costs 60-120 more registers and halves the resident warps:
+// 4096^2 fp32 fell from 1391 to 1150-1232 V-cycles/s. The chained form with 16 warps per SM stays.)
 //
 // Columns/rows outside the grid stay exactly 0 at every stage (Dirichlet rule,
 // cpu-raw.lua:36-39). Lanes near the strip edge compute garbage that never reaches the
@@ -20,7 +25,16 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <type_traits>
+
 #include "mg_math.cuh"
+
+#ifndef MG_WARP2D_MIN_CTAS
+#define MG_WARP2D_MIN_CTAS 4   // resident CTAs (of 4 warps) per SM the register allocation must allow
+#endif
+#ifndef MG_PACKED_F32
+#define MG_PACKED_F32 1       // fp32 stage arithmetic with Blackwell's packed FADD2/FFMA2/FMUL2
+#endif
 
 namespace mg {
 
@@ -57,12 +71,13 @@ template <int S, bool RES> struct Warp2DCfg {
 };
 
 template <typename R, typename A, int S, bool PRO, bool RES>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(128, MG_WARP2D_MIN_CTAS)
 k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f, const R *__restrict__ Vp,
          R *__restrict__ Rout, int L, int TY, int nstrips, int nitems, Coef<A> cf)
 {
     typedef Warp2DCfg<S, RES> C;
     constexpr int NST = C::NST, H = C::H;
+    constexpr bool PACKED = MG_PACKED_F32 != 0 && std::is_same<A, float>::value && std::is_same<R, float>::value;
     const int item = (int)((blockIdx.x * blockDim.x + threadIdx.x) >> 5);
     const int lane = threadIdx.x & 31;
     if (item >= nitems) return;  // warp-uniform
@@ -75,6 +90,8 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
     const int yb = y0 - H, nin = (y1 - y0) + 2 * H;
     const size_t sL = (size_t)L;
     const int L2 = L >> 1;
+    // the strip (with its halo columns) lies inside the grid: no column masks
+    const bool strip_inner = (x0 - C::HX >= 0) && (x0 - C::HX + 128 <= L);
 
     A acc[NST][4], prev[NST][4];
 #pragma unroll
@@ -83,49 +100,95 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
         for (int i = 0; i < 4; ++i) { acc[s][i] = (A)0; prev[s][i] = (A)0; }
     A rpart[2] = {(A)0, (A)0};
 
-    for (int t = 0; t < nin; ++t) {
-        const int q = yb + t;
-        R row[4] = {(R)0, (R)0, (R)0, (R)0};
-        if (xin && q >= 0 && q < L) {
-            load4<R>(src + (size_t)gx0 + sL * (size_t)q, row);
+    // fp32 arithmetic: the source row (and, PRO, its two coarse values) of the NEXT step is fetched while this
+    // step computes, so the global-load latency leaves the row-to-row critical path (+3 % at 4096^2, +10 % on
+    // the PRO pass). With 8-byte accumulators the extra registers spill (-5 % at 2048^2 fp64): there the row is
+    // fetched at the start of its own step.
+    constexpr bool PREFETCH = sizeof(A) == 4;
+    R pre[4] = {(R)0, (R)0, (R)0, (R)0}, pv[2] = {(R)0, (R)0};
+    auto fetch = [&](const int q, const bool ok) {
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pre[i] = (R)0;
+        pv[0] = pv[1] = (R)0;
+        if (ok) {
+            load4<R>(src + (size_t)gx0 + sL * (size_t)q, pre);
             if (PRO) {
                 const R *vp = Vp + (size_t)(gx0 >> 1) + (size_t)L2 * (size_t)(q >> 1);
-                const R v0 = vp[0], v1 = vp[1];
-                row[0] = (R)Ar<A>::add((A)row[0], (A)v0);
-                row[1] = (R)Ar<A>::add((A)row[1], (A)v0);
-                row[2] = (R)Ar<A>::add((A)row[2], (A)v1);
-                row[3] = (R)Ar<A>::add((A)row[3], (A)v1);
+                pv[0] = vp[0]; pv[1] = vp[1];
             }
         }
+    };
+    if (PREFETCH) fetch(yb, xin && yb >= 0 && yb < L);
+
+    // One row step. ST: every stage is fed and emits and every row touched lies inside the grid (and, for
+    // the stages that store, inside [y0, y1)); MK: columns may lie outside the grid.
+    auto step = [&](auto steady_tag, auto masked_tag, const int t) {
+        constexpr bool ST = decltype(steady_tag)::value, MK = decltype(masked_tag)::value;
+        const int q = yb + t;
+        if (!PREFETCH) fetch(q, ST ? (!MK || xin) : (xin && q >= 0 && q < L));
+        R row[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) row[i] = PRO ? (R)Ar<A>::add((A)pre[i], (A)pv[i >> 1]) : pre[i];   // outside the grid: 0 (+ 0)
+        if (PREFETCH) fetch(q + 1, ST ? (!MK || xin) : (xin && q + 1 >= 0 && q + 1 < L));
 #pragma unroll
         for (int sidx = 0; sidx < NST; ++sidx) {
             const int s = sidx + 1;
-            if (t < 2 * sidx) break;           // stage not fed yet (warp-uniform)
-            const bool emit = t >= 2 * s;
+            if (!ST && t < 2 * sidx) break;      // stage not fed yet (warp-uniform)
+            const bool emit = ST ? true : (t >= 2 * s);
             const int p = q - s;                 // row this stage completes now
-            const bool pin = p >= 0 && p < L;
+            const bool pin = ST ? true : (p >= 0 && p < L);
+            const bool keep = pin && (MK ? xin : true);
             const bool is_res = RES && s == NST;
             R fv[4] = {(R)0, (R)0, (R)0, (R)0};
-            if (emit && pin && xin) load4<R>(f + (size_t)gx0 + sL * (size_t)p, fv);
+            if (emit && keep) load4<R>(f + (size_t)gx0 + sL * (size_t)p, fv);
             const R lft = shfl_up1(row[3]), rgt = shfl_dn1(row[0]);
-            R outv[4];
+            A o[4];
+            if constexpr (PACKED) {
+                auto P = [](float a, float b) { return make_float2(a, b); };
+                // xl + xr pairs operands one element apart: scalar adds that land in aligned pairs
+                const float2 sx[2] = {P(__fadd_rn(lft, row[1]), __fadd_rn(row[0], row[2])),
+                                      P(__fadd_rn(row[1], row[3]), __fadd_rn(row[2], rgt))};
+                const float2 Cc[2] = {P(row[0], row[1]), P(row[2], row[3])};
+                const float2 NINV = P(-cf.inv_h2, -cf.inv_h2), INV = P(cf.inv_h2, cf.inv_h2), AD = P(cf.adiag, cf.adiag);
+                const float2 CN = P(cf.cneg, cf.cneg), M1 = P(-1.f, -1.f);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const A xl = (A)(i == 0 ? lft : row[i - 1]), xr = (A)(i == 3 ? rgt : row[i + 1]);
-                const A c = (A)row[i];
-                const A tot = Ar<A>::add(acc[sidx][i], c);                       // pending row gets its y+1
-                const A o = is_res ? residual_point<A>(tot, (A)fv[i], prev[sidx][i], cf)
-                                   : jacobi_point<2, A>(tot, (A)fv[i], cf);
-                outv[i] = (xin && pin) ? (R)o : (R)0;
-                acc[sidx][i] = Ar<A>::add(Ar<A>::add(xl, xr), prev[sidx][i]);    // (xl+xr)+yl of this row
-                prev[sidx][i] = c;
+                for (int k = 0; k < 2; ++k) {
+                    const float2 PRV = P(prev[sidx][2 * k], prev[sidx][2 * k + 1]);
+                    const float2 Tt = __fadd2_rn(P(acc[sidx][2 * k], acc[sidx][2 * k + 1]), Cc[k]);   // pending row gets its y+1
+                    const float2 F = P(fv[2 * k], fv[2 * k + 1]);
+                    float2 ov;
+                    if (is_res) {
+                        const float2 au = __fadd2_rn(__fmul2_rn(Tt, INV), __fmul2_rn(AD, PRV));
+                        ov = __ffma2_rn(au, M1, F);                                                    // f - au
+                    } else {
+                        ov = __fmul2_rn(__ffma2_rn(Tt, NINV, F), CN);    // RN(f - S/h^2) * (-h^2/4): exact scaling (mg_math.cuh)
+                    }
+                    o[2 * k] = ov.x; o[2 * k + 1] = ov.y;
+                    const float2 NA = __fadd2_rn(sx[k], PRV);                                          // (xl+xr)+yl of this row
+                    acc[sidx][2 * k] = NA.x; acc[sidx][2 * k + 1] = NA.y;
+                    prev[sidx][2 * k] = Cc[k].x; prev[sidx][2 * k + 1] = Cc[k].y;
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    const A xl = (A)(i == 0 ? lft : row[i - 1]), xr = (A)(i == 3 ? rgt : row[i + 1]);
+                    const A c = (A)row[i];
+                    const A tot = Ar<A>::add(acc[sidx][i], c);                       // pending row gets its y+1
+                    o[i] = is_res ? residual_point<A>(tot, (A)fv[i], prev[sidx][i], cf)
+                                  : jacobi_point<2, A>(tot, (A)fv[i], cf);
+                    acc[sidx][i] = Ar<A>::add(Ar<A>::add(xl, xr), prev[sidx][i]);    // (xl+xr)+yl of this row
+                    prev[sidx][i] = c;
+                }
             }
             if (!emit) break;
+            R outv[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) outv[i] = (ST && !MK) ? (R)o[i] : (keep ? (R)o[i] : (R)0);
             if (!is_res) {
-                if (s == S && p >= y0 && p < y1 && xst) store4<R>(dst + (size_t)gx0 + sL * (size_t)p, outv);
+                if (s == S && (ST || (p >= y0 && p < y1)) && xst) store4<R>(dst + (size_t)gx0 + sL * (size_t)p, outv);
 #pragma unroll
                 for (int i = 0; i < 4; ++i) row[i] = outv[i];
-            } else if (p >= y0 && p < y1) {
+            } else if (ST || (p >= y0 && p < y1)) {
                 // restriction, children in the reference's order (cpu-raw.lua:62)
                 if ((p & 1) == 0) {
                     rpart[0] = Ar<A>::add((A)outv[0], (A)outv[1]);
@@ -137,7 +200,22 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
                 }
             }
         }
+    };
+
+    // Steady range: every stage emits (t >= 2*NST), the last stage's row q - NST is inside the grid, the
+    // source row q AND the prefetched row q + 1 are inside the grid, and the storing stages' rows are inside
+    // [y0, y1): the last Jacobi stage's row q - S < y1 (its lower bound and the residual stage's follow from
+    // t >= 2*NST and H = NST).
+    const int t_lo = max(2 * NST, NST - yb);
+    const int t_hi = min(min(nin - 1, L - 2 - yb), (y1 - 1) + S - yb);
+    int t = 0;
+    for (; t < min(t_lo, nin); ++t) step(std::false_type{}, std::true_type{}, t);
+    if (strip_inner) {
+        for (; t <= t_hi; ++t) step(std::true_type{}, std::false_type{}, t);
+    } else {
+        for (; t <= t_hi; ++t) step(std::true_type{}, std::true_type{}, t);
     }
+    for (; t < nin; ++t) step(std::false_type{}, std::true_type{}, t);
 }
 
 }  // namespace mg
