@@ -27,8 +27,9 @@
 #define MG_TILE_X 56
 #endif
 #ifndef MG_WARP2D_MIN_TY
-#define MG_WARP2D_MIN_TY 4    // fewest rows per work item of the 2-D smoother: the mid-size levels are latency-bound (rows
-                              // streamed per warp), not work-bound: 4 instead of 16 gave +13 % (4096^2 fp32) / +30 % (2048^2 fp64)
+#define MG_WARP2D_MIN_TY 2    // fewest rows per work item of the 2-D smoother: the mid-size levels are latency-bound (rows
+                              // streamed per warp), not work-bound. Measured 16 / 4 / 2 rows: 2002 / 2287 / 2319 V-cycles/s at
+                              // 4096^2 fp32 and 2285 / 3221 / 3367 at 2048^2 fp64.
 #endif
 #ifndef MG_TILE_Y
 #define MG_TILE_Y 40
