@@ -11,8 +11,10 @@ MultigridCPURaw (cpu-raw.lua:118-258) / MultigridGPU (gpu.lua:18-375): fields si
 smooth, accuracy, debugging; methods init, run, twoGrid, inPlaceIterativeSolver; buffers
 f, psi, psiOld, errorBuf, tmpU, rs[L], Rs[L], vs[L], Vs[L] (device pointers).
 
-NOT EXECUTED in the build environment (no Lua runtime there); the same C ABI is exercised by
-the Python mirror lua-multigrid-poisson_b200/__init__.py. Kept declarative on purpose.
+No LuaJIT exists in the build environment; this file is executed from source by the project's
+own Lua interpreter with an ffi shim (tests/test_lua_binding.py: oracle/minilua.py +
+oracle/minilua_ffi.py), and the same C ABI is exercised by the Python mirror
+lua-multigrid-poisson_b200/__init__.py. Kept declarative on purpose.
 The ffi.cdef text below is the MGPOISSON_CDEF block of include/mgpoisson.h, verbatim.
 --]]
 local ffi = require 'ffi'

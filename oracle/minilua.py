@@ -1117,6 +1117,10 @@ class Interpreter:
         io.set("write", self._io_write)
         g["io"] = io
         g["string"] = STRING_LIB.as_table()
+        import os as _os
+        import time as _time
+        g["os"] = self.table_from({"getenv": lambda k: (_os.environ.get(k),), "clock": lambda: _time.process_time(),
+                                   "time": lambda: float(int(_time.time()))})
         # LuaJIT loads its `bit` library as a global as well (gpu.lua:257 uses it without a require)
         g["bit"] = self.table_from({"lshift": lambda a, n: float(int(a) << int(n)), "rshift": lambda a, n: float(int(a) >> int(n)),
                                     "band": lambda a, b: float(int(a) & int(b)), "bor": lambda a, b: float(int(a) | int(b))})
