@@ -12,8 +12,8 @@ smooth, accuracy, debugging; methods init, run, twoGrid, inPlaceIterativeSolver;
 f, psi, psiOld, errorBuf, tmpU, rs[L], Rs[L], vs[L], Vs[L] (device pointers).
 
 No LuaJIT exists in the build environment; this file is executed from source by the project's
-own Lua interpreter with an ffi shim (tests/test_lua_binding.py: oracle/minilua.py +
-oracle/minilua_ffi.py), and the same C ABI is exercised by the Python mirror
+own Lua interpreter with an ffi shim (tests/test_lua_binding.py; both are test infrastructure
+outside this package), and the same C ABI is exercised by the Python mirror
 lua-multigrid-poisson_b200/__init__.py. Kept declarative on purpose.
 The ffi.cdef text below is the MGPOISSON_CDEF block of include/mgpoisson.h, verbatim.
 --]]
