@@ -177,40 +177,49 @@ def main():
     sys.exit(0 if ok else 1)
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--rings" not in sys.argv:
     main()
 
 
 def check_rings(NST, TZ, NSLOT=3):
-    """Slot/phase bookkeeping of the source ring and the f ring exactly as k_stream3d does it
-    (cursors su/pu, sf/pf; issue at step t of source plane t+NSLOT-1 and f plane t+1)."""
+    """Slot/phase bookkeeping of the source ring and the f ring exactly as k_stream3d does it: cursors su/pu and sf;
+    at step t the TMA thread issues source plane t+2 AND f plane t+1 on ONE mbarrier (the source slot's, expect_tx =
+    two planes); the prologue issues source planes 0, 1 and puts f plane 0 on the mbarrier of source plane 1. Checked:
+    a slot is never refilled while a stage still needs its tenant, the parity every wait uses is the phase that
+    carries the awaited planes, and the single wait of step t (source slot of plane t) also covers the f plane
+    stage 1 reads at step t (plane t-1)."""
+    assert NSLOT == 3
     H = NST
     NF = 2 * NST + 1
     nin, T = TZ + 2 * H, TZ + 3 * H - 1
-    uslot, uloads = [None] * NSLOT, [0] * NSLOT      # tenant plane, number of completed loads
-    fslot, floads = [None] * NF, [0] * NF
+    uslot, uphase = [None] * NSLOT, [0] * NSLOT      # tenant plane; completed phases of the slot's mbarrier
+    bar_f = [None] * NSLOT                          # f plane counted on the current phase of each mbarrier
+    fslot = [None] * NF
     f_last_use = {}
-    for k in range(NSLOT - 1):
-        if k < nin:
-            uslot[k] = k; uloads[k] += 1
-    fslot[0] = 0; floads[0] += 1
-    su, pu, sf, pf = 0, 0, NF - 1, 1
+    f_waited = set()                                # f planes whose mbarrier phase some step has awaited
+    for k in range(NSLOT - 1):                      # prologue
+        uslot[k] = k; uphase[k] += 1
+    fslot[0] = 0; bar_f[1] = 0
+    su, pu, sf = 0, 0, NF - 1
     for t in range(T):
         k = t + NSLOT - 1
         if k < nin:
             ks = NSLOT - 1 if su == 0 else su - 1
             assert ks == k % NSLOT
             assert uslot[ks] is None or uslot[ks] <= t - 1, "source slot still in use"
-            uslot[ks] = k; uloads[ks] += 1
-        j = t + 1
-        if j <= nin - 2:
+            j = t + 1
+            assert j <= nin - 2                      # the two issue conditions are the same condition
             ksf = (sf + 2) % NF
             assert ksf == j % NF
             old = fslot[ksf]
             assert old is None or f_last_use.get(old, -1) < t, ("f slot still in use", t, old)
-            fslot[ksf] = j; floads[ksf] += 1
-        if t < nin:
-            assert uslot[su] == t and (uloads[su] - 1) & 1 == pu, ("source phase", t)
+            uslot[ks] = k; uphase[ks] += 1; bar_f[ks] = j; fslot[ksf] = j
+        else:
+            assert t + 1 > nin - 2
+        if t < nin:                                  # the step's single wait
+            assert uslot[su] == t and (uphase[su] - 1) & 1 == pu, ("source phase", t)
+            if bar_f[su] is not None:
+                f_waited.add(bar_f[su])
         for sidx in range(NST):
             s = sidx + 1
             if not (t >= 3 * sidx and t <= nin + s - 2):
@@ -219,17 +228,20 @@ def check_rings(NST, TZ, NSLOT=3):
                 jj = t - 1 - 2 * sidx
                 kf = (sf - 2 * sidx) % NF
                 assert 1 <= jj <= nin - 2 and fslot[kf] == jj, ("f plane", t, s, jj, fslot[kf])
-                if sidx == 0:
-                    assert (floads[kf] - 1) & 1 == pf, ("f phase", t, jj, floads[kf], pf)
+                assert jj in f_waited, ("f plane read before its mbarrier was awaited", t, s, jj)
                 f_last_use[jj] = t
         su += 1
         if su == NSLOT:
             su, pu = 0, pu ^ 1
         sf += 1
         if sf == NF:
-            sf, pf = 0, pf ^ 1
+            sf = 0
+    assert 0 in f_waited                            # the never-used f plane 0 has landed before the CTA can exit
     return True
 
 
 if __name__ == "__main__" and "--rings" in sys.argv:
-    pass
+    for NST in (1, 2, 3, 4, 5):
+        for TZ in (2, 4, 6, 16, 33, 64):
+            check_rings(NST, TZ)
+    print("ring bookkeeping ok")
