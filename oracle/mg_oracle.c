@@ -18,7 +18,9 @@
  * double and float). The same is done for gpu.lua (oracle/run_reference_gpu.py): its host code
  * runs under minilua on a fake in-memory OpenCL device whose kernels are gpu.lua's own OpenCL C
  * source compiled by gcc (-ffp-contract=off) into oracle/_ref/ -> tests/golden/refgpu_2d_*.npz
- * (real = float there is fp32 ARITHMETIC). tests/test_reference_source.py requires this oracle
+ * (real = float there is fp32 ARITHMETIC), and for cpu.lua (oracle/run_reference_cpu.py, the
+ * variant that re-zeroes the coarse corrections every cycle) -> tests/golden/refcpu_2d_*.npz.
+ * tests/test_reference_source.py requires this oracle
  * to reproduce all those fixtures BIT FOR BIT; tests/test_gpu_vcycle.py requires the same of the
  * CUDA path. Status: the three 2-D modes (f64, f32 storage + f64 arithmetic, f32) are PINNED TO
  * THE REFERENCE SOURCE AS EXECUTED BY minilua (+ gcc for the kernels) -- not by LuaJIT / an

@@ -22,8 +22,9 @@ as numbers, not as text), and the un-vendored libraries `ext`, `image`, whose fe
 
 Supported: local/global variables, assignments (multiple), functions and closures, method definitions and calls
 (`function T:m()`, `obj:m()`), varargs, numeric and generic `for`, `while`, `repeat`, `if/elseif/else`, `do`,
-`return`, `break`, table constructors, all Lua 5.1 operators, metatables limited to `__index` (table or function)
-and `__call`, strings with the usual escapes, long strings/comments. Not supported: coroutines, goto, string
+`return`, `break`, table constructors, all Lua 5.1 operators, the metamethods `__index` (table or function), `__call`,
+`__add __sub __mul __div __mod __pow __unm __concat` (as in Lua 5.1, `#` ignores `__len` on tables), strings with the
+usual escapes, long strings/comments. Not supported: coroutines, goto, string
 library patterns, integer division, bitwise operators (Lua 5.3).
 """
 import math
@@ -502,6 +503,19 @@ class TableCons(Node):
         return t
 
 
+_ARITH_EVENT = {"+": "__add", "-": "__sub", "*": "__mul", "/": "__div", "%": "__mod", "^": "__pow", "..": "__concat"}
+
+
+def _metamethod(a, b, event):
+    """Lua 5.1 manual 2.8: the handler of a binary event is looked up in the first operand, then in the second."""
+    for v in (a, b):
+        if isinstance(v, LuaTable) and v.meta is not None:
+            h = v.meta.get(event)
+            if h is not None:
+                return h
+    return None
+
+
 def _arith_operand(v, line):
     if isinstance(v, bool) or not isinstance(v, (int, float)):
         if isinstance(v, str):
@@ -573,12 +587,21 @@ class BinOp(Node):
             ta, tb = type(a), type(b)
             if (ta is float or ta is int) and (tb is float or tb is int):
                 return fn(a, b)
+            h = _metamethod(a, b, _ARITH_EVENT[op])
+            if h is not None:
+                r = lua_call(h, [a, b])
+                return r[0] if r else None
             return fn(_arith_operand(a, self.line), _arith_operand(b, self.line))
         if op == "==":
             return a == b if not (isinstance(a, bool) ^ isinstance(b, bool)) else False
         if op == "~=":
             return not (a == b if not (isinstance(a, bool) ^ isinstance(b, bool)) else False)
         if op == "..":
+            if not isinstance(a, (str, int, float)) or not isinstance(b, (str, int, float)):
+                h = _metamethod(a, b, "__concat")
+                if h is not None:
+                    r = lua_call(h, [a, b])
+                    return r[0] if r else None
             return lua_tostring(a) + lua_tostring(b)
         if (isinstance(a, (int, float)) and isinstance(b, (int, float))) or (isinstance(a, str) and isinstance(b, str)):
             if op == "<":
@@ -600,6 +623,9 @@ class UnOp(Node):
     def eval(self, scope):
         v = self.e.eval(scope)
         if self.op == "-":
+            if isinstance(v, LuaTable) and v.meta is not None and v.meta.get("__unm") is not None:
+                r = lua_call(v.meta.get("__unm"), [v, v])
+                return r[0] if r else None
             return -_arith_operand(v, self.line)
         if self.op == "not":
             return not lua_truth(v)

@@ -108,6 +108,24 @@ def test_cuda_matches_the_reference_source_run(mgp, path):
     s.close()
 
 
+@pytest.mark.parametrize("path", sorted(glob.glob(os.path.join(HERE, "golden", "refcpu_2d_*.npz"))),
+                         ids=lambda p: os.path.basename(p)[:-4])
+def test_cuda_with_zeroed_corrections_matches_cpu_lua(mgp, path):
+    """refcpu_2d_*.npz = the reference's cpu.lua (coarse corrections re-zeroed every cycle, cpu.lua:138; the solver
+    of test/converge-multigrid-vs-krylov.lua) executed by oracle/minilua.py (oracle/run_reference_cpu.py).
+    mg_zero_corrections() + mg_step(), cycle after cycle, must give the same bits."""
+    g = np.load(path)
+    dim, size, kind, steps = (int(x) for x in g["meta"])
+    s = mgp.MultigridCUDA(size, kind, dim=dim, out=False)
+    assert_bits_equal(s.psi.download().ravel(), g["psi0"], "psi after init")
+    for c in range(steps):
+        s.zero_corrections()
+        e = s.step()
+        assert abs(e - g["errs"][c]) <= err_rtol(size ** dim) * g["errs"][c]
+        assert_bits_equal(s.psi.download().ravel(), g[f"psi{c + 1}"], f"psi after step {c + 1}")
+    s.close()
+
+
 @pytest.mark.parametrize("path", sorted(p for p in glob.glob(os.path.join(HERE, "golden", "*.npz"))
                                         if not os.path.basename(p).startswith("ref")),
                          ids=lambda p: os.path.basename(p)[:-4])
