@@ -143,7 +143,7 @@ def run_reference(size, real="double"):
 
 
 CASES = [  # (size, real, keep the full stage-by-stage trace?)
-    (2, "double", True), (4, "double", True), (8, "double", True), (16, "double", True), (8, "float", True), (16, "float", True),
+    (1, "double", True), (2, "double", True), (4, "double", True), (8, "double", True), (16, "double", True), (8, "float", True), (16, "float", True),
     (32, "double", False), (32, "float", False),   # test/test.lua:45 runs log2size = 5
     (64, "double", False), (64, "float", False),   # BASELINE config 1
 ]
