@@ -195,6 +195,18 @@ local function levelTable(self, which)
 end
 
 function MultigridCUDA:init(size, real, cpuDepth)
+	if type(size) == 'table' then
+		-- cpu.lua:173-181: MultigridCPU{size=, maxiter=, epsilon=, errorCallback=, debug=}, the form
+		-- test/converge-multigrid-vs-krylov.lua:20-29 uses. cpu.lua starts the coarse corrections of
+		-- every cycle from zero (cpu.lua:138), so this form does too.
+		local args = size
+		self.maxiter = args.maxiter or 1000			-- cpu.lua:22
+		self.epsilon = args.epsilon or 1e-10		-- cpu.lua:21
+		self.errorCallback = args.errorCallback
+		if args.debug ~= nil then self.debugging = args.debug end
+		self.zeroCorrections = true
+		size, real, cpuDepth = args.size, args.real, args.cpuDepth
+	end
 	self.real = real or 'double'		-- cpu-raw.lua:143
 	self.size = size
 	local out = ffi.new'mg_ctx*[1]'
@@ -208,7 +220,17 @@ function MultigridCUDA:init(size, real, cpuDepth)
 	end
 	for name,which in pairs{f=lib.MG_BUF_F, psi=lib.MG_BUF_PSI, psiOld=lib.MG_BUF_PSIOLD,
 							errorBuf=lib.MG_BUF_ERRORBUF, tmpU=lib.MG_BUF_TMPU} do
-		self[name] = {buffer = lib.mg_device_ptr(self.handle, which, size)}
+		local mg = self
+		self[name] = {
+			buffer = lib.mg_device_ptr(self.handle, which, size),
+			-- mg.psi:normLInf(), what the convergence experiment records per cycle
+			-- (converge-multigrid-vs-krylov.lua:25), computed on the device
+			normLInf = function()
+				local out = ffi.new'double[1]'
+				check(mg, lib.mg_linf_norm(mg.handle, which, size, out))
+				return out[0]
+			end,
+		}
 	end
 	self.rs = levelTable(self, lib.MG_BUF_r)
 	self.Rs = levelTable(self, lib.MG_BUF_R)
@@ -236,6 +258,7 @@ function MultigridCUDA:twoGrid(h, u, f, L)						-- cpu-raw.lua:186-237
 end
 
 function MultigridCUDA:step()									-- cpu.lua:196-206
+	if self.zeroCorrections then check(self, lib.mg_zero_corrections(self.handle)) end		-- cpu.lua:138
 	local err = ffi.new'double[1]'
 	check(self, lib.mg_step(self.handle, err))
 	return err[0]

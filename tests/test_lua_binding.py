@@ -131,3 +131,40 @@ def test_lua_class_twogrid_and_smoother_on_device_pointers():
     assert names[12:14] == ["f", "u"] and Ls[13] == size
     _bits_equal(psi2.numpy(np.float64), g["t00013"], "psi after 7 Jacobi sweeps")
     ffi.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("size", [16, 32, 64])
+def test_lua_class_in_cpu_lua_style_matches_cpu_lua(size):
+    """The cpu.lua form of the API, as test/converge-multigrid-vs-krylov.lua:20-30 uses it: a table constructor with an
+    errorCallback that records mg.psi:normLInf() per cycle, then :solve(). cpu.lua re-zeroes the coarse corrections
+    every cycle (cpu.lua:138); fixtures tests/golden/refcpu_2d_*.npz are cpu.lua itself executed by minilua."""
+    g = np.load(os.path.join(GOLDEN, f"refcpu_2d_{size}_f64.npz"))
+    steps = int(g["meta"][3])
+    it, ffi, cls = load_binding()
+    src = """
+    local cls, size, steps = ...
+    local data = {}
+    local mg
+    mg = cls{
+        size = size,
+        maxiter = steps,
+        epsilon = 1e-20,
+        errorCallback = function(iter, err)
+            data[iter] = {err, mg.psi:normLInf()}
+        end,
+    }
+    mg:solve()
+    return mg, data
+    """
+    obj, data = it.run(src, "driver", [cls, float(size), float(steps)])
+    lib = ffi.libs[0]
+    assert data.length() == steps
+    for c in range(steps):
+        err, linf = data.get(c + 1).get(1), data.get(c + 1).get(2)
+        w = float(g["errs"][c])
+        assert abs(err - w) <= (1e-12 + size * size * 2.0 ** -55) * w
+        assert linf == float(np.max(np.abs(g[f"psi{c + 1}"])))
+    psi = ml.lua_call(ml.lua_index(obj, "getbuffer"), [obj, lib.lua_index("MG_BUF_PSI"), float(size)])[0]
+    _bits_equal(psi.numpy(np.float64), g[f"psi{steps}"], f"psi after {steps} cycles of solve()")
+    ffi.close()
