@@ -7,8 +7,8 @@ device, and writes what it computes to tests/golden/refgpu_*.npz. TEST INFRASTRU
 What runs what:
   * gpu.lua's Lua host code (MultigridGPU:init, :twoGrid, :run, clcall1D/2D ...) is interpreted by oracle/minilua.py.
   * The OpenCL C kernel source that gpu.lua:36-199 hands to `cl.program` -- after gpu.lua's own template substitution of
-    `size` and `real` -- is compiled BY GCC AS C into oracle/_ref/ (git-ignored; the reference text is never copied into
-    the repository) behind a four-line prelude: `kernel` and `global` are empty qualifiers and get_global_id /
+    `size` and `real` -- is piped to GCC and compiled AS C into oracle/_ref/*.so (git-ignored; the reference text itself
+    is never written into the repository tree) behind a four-line prelude: `kernel` and `global` are empty qualifiers and get_global_id /
     get_global_size read the work-item index the launcher sets. Flags: -O2 -ffp-contract=off, i.e. every operator
     correctly rounded and nothing contracted -- the strict reading of OpenCL C (a real device may contract a*b+c and
     may divide with <= 2.5 ulp error, so a GPU run of the reference is only defined up to that; this is the one
@@ -150,10 +150,10 @@ class FakeCL:
         size = int(re.search(r"#define\s+size\s+(\d+)", code).group(1))
         os.makedirs(REFDIR, exist_ok=True)
         base = os.path.join(REFDIR, f"gpu_kernels_{self.real}_{size}")
-        with open(base + ".c", "w") as fh:
-            fh.write(PRELUDE + code)
-        subprocess.run(["gcc", "-std=gnu11", "-O2", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas", "-shared", "-fPIC",
-                        "-o", base + ".so", base + ".c", "-lm"], check=True)
+        # the kernel text goes to gcc through a pipe: only the compiled object lands in oracle/_ref/, the reference's
+        # source is never written into the repository tree
+        subprocess.run(["gcc", "-x", "c", "-std=gnu11", "-O2", "-ffp-contract=off", "-fno-fast-math", "-Wno-unknown-pragmas",
+                        "-shared", "-fPIC", "-o", base + ".so", "-", "-lm"], input=(PRELUDE + code).encode(), check=True)
         self.lib = C.CDLL(base + ".so")
         self.gid = (C.c_int * 3).in_dll(self.lib, "mg_gid")
         self.gsz = (C.c_int * 3).in_dll(self.lib, "mg_gsz")
