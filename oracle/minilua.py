@@ -30,11 +30,19 @@ library patterns, integer division, bitwise operators (Lua 5.3).
 import math
 import re
 
-__all__ = ["LuaError", "LuaTable", "LuaFunction", "Interpreter", "lua_call", "lua_index", "lua_setindex", "lua_truth"]
+__all__ = ["LuaError", "LuaExit", "LuaTable", "LuaFunction", "Interpreter", "lua_call", "lua_index", "lua_setindex", "lua_truth"]
 
 
 class LuaError(Exception):
     pass
+
+
+class LuaExit(Exception):
+    """os.exit(code)"""
+
+    def __init__(self, code):
+        super().__init__(code)
+        self.code = code
 
 
 class _Break(Exception):
@@ -1115,9 +1123,11 @@ class Interpreter:
     """Global environment with the part of the base library the reference touches. `modules` maps `require` names to
     values (LuaTable, Python callable, ...); a missing module raises, like Lua's require."""
 
-    def __init__(self, modules=None, stdout=None):
+    def __init__(self, modules=None, stdout=None, search_dirs=()):
         self.globals = Scope()
         self.modules = dict(modules or {})
+        self.search_dirs = list(search_dirs)   # `require 'a.b'` also tries <dir>/a/b.lua (after package.path's ?.lua entries)
+        self.loaded = {}
         self.printed = []      # every print(...) call as a tuple of raw values
         self.written = []      # io.write arguments
         self._stdout = stdout
@@ -1126,6 +1136,9 @@ class Interpreter:
         g["error"] = self._error
         g["assert"] = self._assert
         g["require"] = self._require
+        g["pcall"] = self._pcall
+        self.package = self.table_from({"path": "./?.lua"})
+        g["package"] = self.package
         g["type"] = self._type
         g["tostring"] = lua_tostring
         g["tonumber"] = self._tonumber
@@ -1145,8 +1158,10 @@ class Interpreter:
         g["string"] = STRING_LIB.as_table()
         import os as _os
         import time as _time
+        def _exit(code=0):
+            raise LuaExit(int(code or 0))
         g["os"] = self.table_from({"getenv": lambda k: (_os.environ.get(k),), "clock": lambda: _time.process_time(),
-                                   "time": lambda: float(int(_time.time()))})
+                                   "time": lambda: float(int(_time.time())), "exit": _exit})
         # LuaJIT loads its `bit` library as a global as well (gpu.lua:257 uses it without a require)
         g["bit"] = self.table_from({"lshift": lambda a, n: float(int(a) << int(n)), "rshift": lambda a, n: float(int(a) >> int(n)),
                                     "band": lambda a, b: float(int(a) & int(b)), "bor": lambda a, b: float(int(a) | int(b))})
@@ -1211,9 +1226,28 @@ class Interpreter:
         return (v, msg) + rest
 
     def _require(self, name):
-        if name not in self.modules:
-            raise LuaError(f"module '{name}' not found")
-        return self.modules[name]
+        if name in self.modules:
+            return self.modules[name]
+        if name in self.loaded:
+            return self.loaded[name]
+        import os as _os
+        rel = name.replace(".", _os.sep)
+        cands = [t.replace("?", rel) for t in str(self.package.get("path") or "").split(";") if t]
+        cands += [_os.path.join(d, rel + ".lua") for d in self.search_dirs]
+        if "." in name:   # LuaJIT-style flat layouts: 'multigrid-poisson.cpu-raw' -> <dir>/cpu-raw.lua
+            cands += [_os.path.join(d, name.split(".")[-1] + ".lua") for d in self.search_dirs]
+        for c in cands:
+            if _os.path.isfile(c):
+                r = self.run_file(c)
+                self.loaded[name] = r[0] if r else True
+                return self.loaded[name]
+        raise LuaError(f"module '{name}' not found")
+
+    def _pcall(self, f=None, *args):
+        try:
+            return (True,) + tuple(lua_call(f, list(args)))
+        except LuaError as e:
+            return (False, str(e))
 
     def _type(self, v):
         if v is None:

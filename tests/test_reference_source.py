@@ -294,3 +294,24 @@ def test_minilua_errors_are_reported_not_swallowed():
         _run("local x = 1 +")
     with pytest.raises(ml.LuaError):
         _run("return require 'no.such.module'")
+
+
+@pytest.mark.skipif(not os.path.exists("/root/reference/cpu-raw.lua"), reason="reference tree not present (GPU box)")
+def test_luajit_timing_hook_runs_and_skips_cleanly():
+    """baseline/run_cpu_raw.lua is meant for a machine that HAS LuaJIT; here it is at least executed by minilua: with
+    the dependency shims it runs the reference and prints its timing line, without them it prints SKIP and exits 0."""
+    import run_reference as rr
+    hook = os.path.join(ROOT, "baseline", "run_cpu_raw.lua")
+    out = io.StringIO()
+    it = ml.Interpreter(modules={"ffi": rr._ffi(), "bit": rr._bit(), "image": rr._image, "ext.class": rr._class,
+                                 "ext.math": rr._ext_math()}, stdout=out)
+    it.globals.vars["arg"] = ml.Interpreter.table_from({1: "8", 2: "double", 3: "/root/reference"})
+    it.run_file(hook)
+    lines = out.getvalue().splitlines()
+    assert lines[-1].startswith("cpu-raw.lua 8 double seconds_for_run ")
+    assert "6828.1698388918" in out.getvalue()                 # the reference's own print(iter, err) of cycle 2
+    out2 = io.StringIO()
+    it2 = ml.Interpreter(modules={"ffi": rr._ffi()}, stdout=out2)
+    with pytest.raises(ml.LuaExit) as e:
+        it2.run_file(hook)
+    assert e.value.code == 0 and out2.getvalue().startswith("SKIP: ")
