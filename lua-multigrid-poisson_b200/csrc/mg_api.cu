@@ -40,6 +40,10 @@ static int create_common(int dim, int size, int real_kind, int smooth, int devic
         g_create_error = "mg_create: bad real_kind";
         return MG_EINVAL;
     }
+    if (smooth < 0 || smooth > 4096) {
+        g_create_error = "mg_create: smooth must be 0 (= the reference's 7) .. 4096";
+        return MG_EINVAL;
+    }
     mg_ctx *c = new (std::nothrow) mg_ctx();
     if (!c) return MG_ENOMEM;
     int rc = c->init(dim, size, real_kind, smooth, device, rank, nranks);
@@ -91,6 +95,7 @@ int mg_set_tuning(mg_ctx *ctx, int tb, int small_L, int use_graph)
 {
     CTX_OR_FAIL(ctx);
     if (tb > 4) return ctx->fail(MG_EINVAL, "tb must be 0..4");
+    if (tb == 0 && ctx->group) return ctx->fail(MG_EINVAL, "tb must be 1..4 on a slab handle (the slab schedule needs the streaming smoother)");
     if (small_L > (1 << (SMALL_MAX_LEVELS - 1))) return ctx->fail(MG_EINVAL, "small_L too large");
     if (tb >= 0) ctx->tb = tb;
     if (small_L >= 0) ctx->small_L = small_L;
@@ -104,7 +109,11 @@ int mg_set_option(mg_ctx *ctx, const char *name, int value)
     CTX_OR_FAIL(ctx);
     if (!name) return MG_EINVAL;
     std::string n(name);
-    if (n == "tb") { if (value < 0 || value > 4) return ctx->fail(MG_EINVAL, "tb must be 0..4"); ctx->tb = value; }
+    if (n == "tb") {
+        if (value < 0 || value > 4) return ctx->fail(MG_EINVAL, "tb must be 0..4");
+        if (value == 0 && ctx->group) return ctx->fail(MG_EINVAL, "tb must be 1..4 on a slab handle (the slab schedule needs the streaming smoother)");
+        ctx->tb = value;
+    }
     else if (n == "small_L") { if (value < 1 || value > (1 << (SMALL_MAX_LEVELS - 1))) return ctx->fail(MG_EINVAL, "bad small_L"); ctx->small_L = value; }
     else if (n == "graph") ctx->use_graph = value != 0;
     else if (n == "stream_min_L") ctx->stream_min_L = value < 64 ? 64 : value;
@@ -117,13 +126,17 @@ int mg_set_option(mg_ctx *ctx, const char *name, int value)
             m->u_ghost_dirty = m->f_ghost_dirty = true;
         }
     }
-    else if (n == "tile_y") ctx->tile_y_opt = value;
     else if (n == "lockstep") ctx->lockstep_opt = value;
+    else if (n == "fastdiv") ctx->fastdiv_opt = value;
+    else if (n == "fast_min_L") ctx->fast_min_L = value;
     else if (n == "slab_graph") ctx->slab_graph_opt = value != 0;
     else if (n == "tma_promo") { ctx->tma_promo = value; ctx->tmaps.clear(); }
     else if (n == "tb2") { if (value < 0 || value > 7) return ctx->fail(MG_EINVAL, "tb2 must be 0..7"); ctx->tb2 = value; }
     else if (n == "warp2d_min_L") ctx->warp2d_min_L = value < 32 ? 32 : value;
-    else if (n == "ty") ctx->ty_override = value;
+    else if (n == "ty") {   // rows per work item of the 2-D smoother: 0 = cost model, else even and >= 2
+        if (value != 0 && (value < 2 || (value & 1))) return ctx->fail(MG_EINVAL, "ty must be 0 (automatic) or an even number >= 2");
+        ctx->ty_override = value;
+    }
     else return ctx->fail(MG_EINVAL, "mg_set_option: unknown option");
     ctx->drop_graph();
     return MG_OK;
@@ -423,18 +436,19 @@ int mg_time_vcycles(mg_ctx *ctx, int n, float *ms_total)
 {
     CTX_OR_FAIL(ctx);
     if (n < 1 || !ms_total) return MG_EINVAL;
-    cudaEvent_t e0, e1;
-    MG_CK(ctx, cudaEventCreate(&e0));
-    MG_CK(ctx, cudaEventCreate(&e1));
-    MG_CK(ctx, cudaStreamSynchronize(ctx->stream));
-    MG_CK(ctx, cudaEventRecord(e0, ctx->stream));
+    cudaEvent_t e0 = nullptr, e1 = nullptr;
     int rc = MG_OK;
-    for (int i = 0; i < n && rc == MG_OK; ++i) rc = ctx->vcycle();
-    MG_CK(ctx, cudaEventRecord(e1, ctx->stream));
-    MG_CK(ctx, cudaEventSynchronize(e1));
-    MG_CK(ctx, cudaEventElapsedTime(ms_total, e0, e1));
-    cudaEventDestroy(e0);
-    cudaEventDestroy(e1);
+    cudaError_t e = cudaEventCreate(&e0);
+    if (e == cudaSuccess) e = cudaEventCreate(&e1);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e == cudaSuccess) e = cudaEventRecord(e0, ctx->stream);
+    for (int i = 0; e == cudaSuccess && i < n && rc == MG_OK; ++i) rc = ctx->vcycle();
+    if (e == cudaSuccess) e = cudaEventRecord(e1, ctx->stream);
+    if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+    if (e == cudaSuccess) e = cudaEventElapsedTime(ms_total, e0, e1);
+    if (e0) cudaEventDestroy(e0);
+    if (e1) cudaEventDestroy(e1);
+    if (e != cudaSuccess) return ctx->fail_cuda(e, "mg_time_vcycles");
     return rc;
 }
 
@@ -520,7 +534,13 @@ int mg_create_slab_local(int dim, int size, int real_kind, int smooth, int devic
         mg_ctx *c = nullptr;
         int rc = create_common(dim, size, real_kind, smooth, device, r, nslabs, &c);
         if (rc) {
-            for (mg_ctx *m : g->m) { m->release(); delete m; }
+            for (size_t k = 0; k < g->m.size(); ++k) {
+                mg_ctx *m = g->m[k];
+                m->group = nullptr;
+                if (k > 0) m->own_stream = nullptr;   // shared with member 0, which destroys it
+                m->release();
+                delete m;
+            }
             delete g; *out = nullptr;
             return rc;
         }

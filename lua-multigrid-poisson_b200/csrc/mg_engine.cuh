@@ -3,6 +3,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -41,6 +42,7 @@ constexpr int MAX_LEVELS = 24;
 constexpr size_t ARENA_ALIGN = 1024;
 constexpr size_t ARENA_HEADER = 1024;   // slab handshake words (Stream3DArgs::hs): [0] passes done,
                                         // [16]/[32] passes published by the lower/upper neighbour, [48] CTAs done
+constexpr size_t ARENA_REDO_OFF = 512;  // Stream3DArgs::redo: {guarded re-run requested, CTA arrival counter}
 
 struct TraceRec {
     char name;
@@ -78,10 +80,11 @@ struct mg_ctx {
     int ty_override = 0;     // 2-D: rows per warp work item (0 = cost model)
     int stream_min_L = 128;  // smallest level width handled by the streaming (TMA) smoother
     int num_sms = 148;       // SM count of the device (queried at init)
-    int tile_y_opt = 0;      // 0 = automatic, else force the float tile's y extent (24 or 22)
-    int lockstep_opt = 0;    // lock-step column mode of the streaming smoother (off: measured slower)
-    int tma_promo = 3;       // L2 promotion of the TMA descriptors: 0 none, 1 64 B, 2 128 B, 3 256 B
+    int lockstep_opt = 1;    // lock-step partition of the streaming smoother: whole columns below zsplit + helper CTAs above
+    int tma_promo = 0;       // L2 promotion of the TMA descriptors: 0 none (least DRAM over-fetch), 1 64 B, 2 128 B, 3 256 B
     int stream_flags = 0;    // debug switches of the streaming smoother (see Stream3DArgs::flags)
+    int fastdiv_opt = 1;     // fp32 streaming smoother: branch-free division kernel + guarded re-run kernel (0: guarded kernel only)
+    int fast_min_L = 256;    // ... at levels at least this wide (128^3: the second launch costs what the branches cost)
     int tz_override = 0;     // planes per CTA of the streaming smoother (0 = cost model)
     // TMA descriptors of the source fields, keyed by (pointer, level width, box x, box y)
     std::map<std::tuple<const void *, int, int, int, int>, CUtensorMap> tmaps;
@@ -345,43 +348,18 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
     // n sweeps starting from `cur` (ping-pong with `oth`), the first optionally reading
     // cur + prolong(Vp), followed optionally by Rout = restrict(f - A cur).
     // ---- streaming (TMA, temporally blocked) smoother passes, 3-D only
-    // the y extent of the float tile is chosen per launch (see pick_tile_y)
     static constexpr int kTileX = sizeof(R) == 4 ? MG_TILE_X : 32;
-    static constexpr int kTileYA = sizeof(R) == 4 ? MG_TILE_Y : 32, kTileYB = kTileYA;   // (88 x 22 tried: see below)
-    // Lock-step mode: when the tile columns of a level fit the resident CTAs almost exactly
-    // (>= 90 %), give every CTA one whole column: all columns then march through z together and
-    // the halo rows neighbouring tiles share are served from L2 instead of HBM. At 512^2 planes a
-    // tile of 88 x 22 gives 6 x 24 = 144 columns for 148 SMs; 88 x 24 gives 132 (89 %).
-    // MEASURED (512^3): lock-step 88 x 22 = 242 V-cycles/s against balanced 88 x 24 = 260; again with the
-    // 56 x 40 tile (130 columns): 203 against 325. The passes are not HBM-bound, so the balanced
-    // partition stays the default ("lockstep" = 0).
-    static int pick_tile_y(mg_ctx *c, int L, bool *lockstep)
-    {
-        *lockstep = false;
-        if (c->tile_y_opt == kTileYA || c->tile_y_opt == kTileYB) {
-            const long t = (long)((L + kTileX - 1) / kTileX) * ((L + c->tile_y_opt - 1) / c->tile_y_opt);
-            *lockstep = c->lockstep_opt != 0 && t <= c->num_sms;
-            return c->tile_y_opt;
-        }
-        if (c->lockstep_opt == 0) return kTileYA;
-        for (int ty : {kTileYA, kTileYB}) {
-            const long t = (long)((L + kTileX - 1) / kTileX) * ((L + ty - 1) / ty);
-            if (t <= c->num_sms && t * 10 >= (long)c->num_sms * 9) { *lockstep = true; return ty; }
-        }
-        return kTileYA;
-    }
+    static constexpr int kTileY = sizeof(R) == 4 ? MG_TILE_Y : 32;
+    // History of the partition (512^3 fp32, V-cycles/s): whole columns only, 88 x 22 tile (144 columns for 148 SMs):
+    // 242; balanced shares of tile x plane work (neighbouring columns staggered in z, halo rows re-fetched from HBM):
+    // 260 -> 326 after the round-1 tuning; round 2: whole columns below zsplit + helper CTAs above (see below).
     template <int S, bool PRO, bool RES>
     int launch_stream3d(mg_ctx *c, int lv, R *dst, const R *src, const R *f, const R *Vp, R *Rout, const Coef<A> &cf)
     {
-        bool lockstep = false;
-        const int ty = pick_tile_y(c, 1 << lv, &lockstep);
-        if (ty == kTileYB && kTileYB != kTileYA)
-            return launch_stream3d_t<S, PRO, RES, kTileYB>(c, lv, dst, src, f, Vp, Rout, cf, lockstep);
-        return launch_stream3d_t<S, PRO, RES, kTileYA>(c, lv, dst, src, f, Vp, Rout, cf, lockstep);
+        return launch_stream3d_t<S, PRO, RES, kTileY>(c, lv, dst, src, f, Vp, Rout, cf);
     }
     template <int S, bool PRO, bool RES, int TY>
-    int launch_stream3d_t(mg_ctx *c, int lv, R *dst, const R *src, const R *f, const R *Vp, R *Rout, const Coef<A> &cf,
-                          bool lockstep)
+    int launch_stream3d_t(mg_ctx *c, int lv, R *dst, const R *src, const R *f, const R *Vp, R *Rout, const Coef<A> &cf)
     {
         const int L = 1 << lv;
         // In-plane tile. 4-byte reals: 56 x 40 (+ halo = 64 wide): 16 vectors per row and a 256-byte row
@@ -406,7 +384,20 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             vz_off = c->dist[lv - 1] ? c->G - zg0 / 2 : 0;
         }
         const int nown = nz_hi - nz_lo;
-        auto kern = k_stream3d<R, A, S, PRO, RES, TX, TY>;
+        // fp32 arithmetic, L >= fast_min_L: the branch-free kernel followed by its (normally empty) guarded re-run
+        // kernel (mg_stream3d.cuh, MODE); everything else: the guarded kernel alone.
+        constexpr bool HAS_FAST = kPackedF32 && std::is_same<R, float>::value && std::is_same<A, float>::value;
+        const bool fast = HAS_FAST && c->fastdiv_opt != 0 && L >= c->fast_min_L;
+        typedef void (*Kern)(const CUtensorMap, const CUtensorMap, Stream3DArgs<R>, Coef<A>);
+        Kern kern = k_stream3d<R, A, S, PRO, RES, TX, TY, S3_GUARDED>, kern2 = nullptr;
+        if constexpr (HAS_FAST) {
+            if (fast) {
+                kern = k_stream3d<R, A, S, PRO, RES, TX, TY, S3_FAST>;
+                kern2 = k_stream3d<R, A, S, PRO, RES, TX, TY, S3_RERUN>;
+                MG_CK(c, cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+                MG_CK(c, cudaFuncSetAttribute(kern2, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+            }
+        }
         MG_CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
         // One CTA per SM, each given an equal share of the tile x plane-pair work (balanced
         // persistent partition inside the kernel); "tz" asks for ~tz planes per share instead.
@@ -419,8 +410,6 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         long ncta;
         if (c->tz_override > 0) {
             ncta = (work + c->tz_override - 1) / c->tz_override;
-        } else if (lockstep) {
-            ncta = tiles;   // one whole column per CTA (the balanced partition degenerates to this)
         } else if (S <= 2) {
             // Shallow passes are HBM-bound: keep whole tile columns marching through z in lock
             // step, so that the halo rows neighbouring tiles share are still in L2 when the
@@ -442,9 +431,29 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         }
         if (ncta < 1) ncta = 1;
         if (ncta > work / 2) ncta = work / 2 > 0 ? work / 2 : 1;
+        // Lock-step partition ("lockstep" option, default on): when there are fewer tile columns than CTAs (but
+        // at least 70 % as many), the first `tiles` CTAs take one whole column each over the planes below zsplit
+        // and march through z together -- the halo rows and partly used sectors that neighbouring tiles share are
+        // then served by L2 instead of HBM (512^3: DRAM reads 2.2 -> 1.28 GB per pass, compulsory 1.07) -- and the
+        // other CTAs share the planes above the split in equal parts. zsplit balances the two groups: a column
+        // costs zs + OV steps, a helper CTA its planes plus OV per chunk (OV = fill/drain steps of the pipeline).
+        int zsplit = 0;
+        if (c->lockstep_opt != 0 && c->tz_override <= 0 && S >= 3 && tiles < ncta && tiles * 10 >= ncta * 7 && nown >= 32) {
+            const int OV = 3 * C::H - 1;
+            const long nh = ncta - tiles;
+            double bestc = 1e30;
+            for (int zs = nown; zs >= nown / 2; zs -= 2) {
+                const double planes = (double)tiles * (nown - zs) / nh;
+                const double chunks = zs == nown ? 0.0 : (double)tiles / nh + 1.0;
+                const double cost = std::max((double)(zs + OV), planes + chunks * OV);
+                if (cost < bestc) { bestc = cost; zsplit = zs; }
+            }
+            if (zsplit >= nown) zsplit = 0;
+        }
         dim3 grid((unsigned)ncta, 1, 1);
         Stream3DArgs<R> a{dst, Vp, Rout, L, c->stream_flags, nz_lo, nz_hi, zdom0, zdom0 + L, rz_off, vz_off,
-                          nullptr, nullptr, nullptr, nullptr, c->G, nullptr, nullptr, nullptr};
+                          nullptr, nullptr, nullptr, nullptr, c->G, nullptr, nullptr, nullptr, zsplit,
+                          (unsigned int *)((char *)c->arena + ARENA_REDO_OFF)};
         if (c->dist[lv] && c->p2p) {  // fused halo exchange: same offsets inside the neighbours' arenas
             const size_t doff = c->arena_off(dst);
             if (c->peer_lo) a.peer_lo = (R *)(c->peer_lo + doff);
@@ -462,6 +471,10 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         }
         c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : (RES ? MG_K_SWEEP_RESTRICT : MG_K_SWEEP), L, S);
         kern<<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(*map, *fmap, a, cf);
+        if (kern2) {
+            MG_LAUNCH_CHECK(c);
+            kern2<<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(*map, *fmap, a, cf);
+        }
         c->prof_end();
         MG_LAUNCH_CHECK(c);
         return MG_OK;
@@ -483,23 +496,29 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
 #undef MG_S3D
         return c->fail(MG_EINVAL, "stream3d_pass: unsupported combination");
     }
-    // split n sweeps into passes of <= tb sweeps; with a fused residual stage the last pass has <= 3
-    static int plan_passes(int n, int tb, bool has_res, int *plan)
+    // split n sweeps into passes of <= tb sweeps; with a fused residual stage the last pass has <= 3.
+    // extra_pass: one pass more than necessary (the slab schedule uses it to make the number of
+    // ping-pong passes of a level visit even, so that the result lands in u without a copy).
+    static std::vector<int> plan_passes(int n, int tb, bool has_res, bool extra_pass = false)
     {
-        int np = 0, rem = n, last = 0;
+        std::vector<int> plan;
+        if (tb < 1) tb = 1;
+        int rem = n, last = 0;
         if (has_res) { last = n < 3 ? n : 3; if (last > tb) last = tb; rem = n - last; }
         if (rem > 0) {
-            int k = (rem + tb - 1) / tb, base = rem / k, extra = rem % k;
-            for (int i = 0; i < k; ++i) plan[np++] = base + (i < extra ? 1 : 0);
+            int k = (rem + tb - 1) / tb;
+            if (extra_pass && k < rem) ++k;
+            const int base = rem / k, extra = rem % k;
+            for (int i = 0; i < k; ++i) plan.push_back(base + (i < extra ? 1 : 0));
         }
-        if (has_res) plan[np++] = last;
-        return np;
+        if (has_res) plan.push_back(last);
+        return plan;
     }
     int sweeps_stream3d(mg_ctx *c, int lv, R *&cur, R *&oth, const R *f, const Coef<A> &cf, int n,
                         const R *Vp, R *Rout)
     {
-        int plan[64];
-        const int np = plan_passes(n, c->tb, Rout != nullptr, plan);
+        const std::vector<int> plan = plan_passes(n, c->tb, Rout != nullptr);
+        const int np = (int)plan.size();
         for (int i = 0; i < np; ++i) {
             int rc = stream3d_pass(c, lv, plan[i], i == 0 && Vp, i == np - 1 && Rout, oth, cur, f, Vp, Rout, cf);
             if (rc) return rc;
@@ -582,8 +601,11 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
                     rc = twogrid_fused(c, h, at(c, u_off), at(c, f_off), lv);
                     c->stream = saved; c->capturing = false;
                     cudaError_t e = cudaStreamEndCapture(c->cap_stream, &c->rep_graph);
-                    if (rc) return rc;
-                    if (e != cudaSuccess) return c->fail_cuda(e, "cudaStreamEndCapture (replicated levels)");
+                    if (rc || e != cudaSuccess) {
+                        if (c->rep_graph) cudaGraphDestroy(c->rep_graph);
+                        c->rep_graph = nullptr;
+                        return rc ? rc : c->fail_cuda(e, "cudaStreamEndCapture (replicated levels)");
+                    }
                     MG_CK(c, cudaGraphInstantiate(&c->rep_gexec, c->rep_graph, 0));
                     size_t nn = 0;
                     MG_CK(c, cudaGraphGetNodes(c->rep_graph, nullptr, &nn));
@@ -602,14 +624,21 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             const size_t W_off = c0->arena_off(c0->W[lv]);
             const size_t Rc_off = c0->arena_off(c0->R[lv - 1]), Vc_off = c0->arena_off(c0->V[lv - 1]);
             size_t cur = u_off, oth = W_off;
-            int plan[64];
+            // The passes ping-pong u <-> W[lv]. With the fused halo exchange the ghost planes of the
+            // field a pass writes are filled by the NEIGHBOURS' kernels, so the result must end up in u
+            // by itself: a trailing copy W -> u would read ghost planes the neighbour may not have
+            // written yet (no handshake covers a memcpy). An odd pass count (smooth = 4 or 8 with
+            // tb = 4) therefore gets one extra post-smoothing pass.
+            const std::vector<int> pre = plan_passes(c0->smooth, c0->tb, true);
+            std::vector<int> post = plan_passes(c0->smooth, c0->tb, false);
+            if ((pre.size() + post.size()) & 1) post = plan_passes(c0->smooth, c0->tb, false, true);
             // pre-smoothing, residual + restriction fused into the last pass (cpu-raw.lua:198-218)
-            int np = plan_passes(c0->smooth, c0->tb, true, plan);
+            int np = (int)pre.size();
             for (int i = 0; i < np; ++i) {
                 const bool res = i == np - 1;
-                if ((rc = slab_exchange(g, cur, lv, plan[i] + (res ? 1 : 0)))) return rc;
+                if ((rc = slab_exchange(g, cur, lv, pre[i] + (res ? 1 : 0)))) return rc;
                 for (mg_ctx *c : g->m)
-                    if ((rc = stream3d_pass(c, lv, plan[i], false, res, (R *)at(c, oth), (const R *)at(c, cur),
+                    if ((rc = stream3d_pass(c, lv, pre[i], false, res, (R *)at(c, oth), (const R *)at(c, cur),
                                             (const R *)at(c, f_off), nullptr, res ? (R *)at(c, Rc_off) : nullptr, cf)))
                         return rc;
                 size_t t = cur; cur = oth; oth = t;
@@ -621,18 +650,25 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             if ((rc = slab_twogrid(g, 2 * h, Vc_off, Rc_off, lv - 1))) return rc;   // cpu-raw.lua:221-222
             if (c0->dist[lv - 1] && (rc = slab_exchange(g, Vc_off, lv - 1, 2))) return rc;
             // prolongation + add fused into the first post-smoothing pass (cpu-raw.lua:225-236)
-            np = plan_passes(c0->smooth, c0->tb, false, plan);
+            np = (int)post.size();
             for (int i = 0; i < np; ++i) {
-                if ((rc = slab_exchange(g, cur, lv, plan[i]))) return rc;
+                if ((rc = slab_exchange(g, cur, lv, post[i]))) return rc;
                 for (mg_ctx *c : g->m)
-                    if ((rc = stream3d_pass(c, lv, plan[i], i == 0, false, (R *)at(c, oth), (const R *)at(c, cur),
+                    if ((rc = stream3d_pass(c, lv, post[i], i == 0, false, (R *)at(c, oth), (const R *)at(c, cur),
                                             (const R *)at(c, f_off), i == 0 ? (const R *)at(c, Vc_off) : nullptr, nullptr, cf)))
                         return rc;
                 size_t t = cur; cur = oth; oth = t;
             }
-            if (cur != u_off)
-                for (mg_ctx *c : g->m)
-                    MG_CK(c, cudaMemcpyAsync(at(c, u_off), at(c, cur), c->level_bytes(lv), cudaMemcpyDeviceToDevice, c0->stream));
+            if (cur != u_off) {
+                // only reachable with smooth = 1 pass plans that cannot be padded: copy the OWNED planes and have
+                // the ghosts refreshed by an explicit exchange before the next pass reads them
+                for (mg_ctx *c : g->m) {
+                    const size_t o = c->own_off_elems(lv) * c->elem;
+                    MG_CK(c, cudaMemcpyAsync(at(c, u_off) + o, at(c, cur) + o, c->own_elems(lv) * c->elem,
+                                             cudaMemcpyDeviceToDevice, c0->stream));
+                }
+                if ((rc = slab_exchange(g, u_off, lv, c0->G, true))) return rc;
+            }
             return MG_OK;
         } else {
             return c0->fail(MG_EUNSUPPORTED, "slab decomposition is 3-D only");
@@ -898,10 +934,11 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         if (c->group) return c->fail(MG_EUNSUPPORTED, "mg_cg: single-GPU only");
         const int top = c->nlevels - 1, L = c->size;
         const size_t n = c->N;
-        if (!c->cg_tmp) MG_CK(c, cudaMalloc(&c->cg_tmp, n * c->elem + 2 * sizeof(double) * (size_t)c->npartial + sizeof(double) * CG_NSCAL));
+        const size_t field_bytes = (n * c->elem + 7) / 8 * 8;   // the double partials behind the field stay 8-byte aligned
+        if (!c->cg_tmp) MG_CK(c, cudaMalloc(&c->cg_tmp, field_bytes + 2 * sizeof(double) * (size_t)c->npartial + sizeof(double) * CG_NSCAL));
         R *x = (R *)c->psi, *r = (R *)c->W[top], *p = (R *)c->psiOld, *Ap = (R *)c->cg_tmp;
         const R *b = (const R *)c->f;
-        double *part2 = (double *)((char *)c->cg_tmp + n * c->elem), *scal = part2 + 2 * c->npartial;
+        double *part2 = (double *)((char *)c->cg_tmp + field_bytes), *scal = part2 + 2 * c->npartial;
         double *partA = c->d_partial, *partB = part2;
         const A inv_h2 = make_coef<A>(DIM, 1.0 / L).inv_h2;
         const int nb = c->npartial;

@@ -61,6 +61,14 @@
 #ifndef MG_PACKED_F32
 #define MG_PACKED_F32 1       // fp32 stage arithmetic with Blackwell's packed FADD2/FFMA2/FMUL2
 #endif
+#ifndef MG_STREAM_DEFER
+#define MG_STREAM_DEFER 1     // fp32: ring stores of a step are issued together at its end (from the carry registers), so
+                              // that no shared-memory store separates one stage's loads from the previous stage's work
+#endif
+#ifndef MG_STREAM_EARLY
+#define MG_STREAM_EARLY 0     // fp32: the next stage's inputs are requested before the current stage's division guard
+                              // (1: neighbour rows + shuffles, 2: also its f rows)
+#endif
 #ifndef MG_STEADY_UNROLL
 #define MG_STEADY_UNROLL 2    // unroll factor of the steady-state step loop
 #endif
@@ -143,7 +151,27 @@ __device__ __forceinline__ double lds1(uint32_t addr, double)
 }
 
 // ------------------------------------------------------------------ vector access
+#ifndef MG_F32_VX
+#define MG_F32_VX 4           // fp32 points per thread and row: 4 (128-bit accesses, 8 points per thread) or 2 (64-bit, 4 points)
+#endif
 template <typename R> struct Vec;
+#if MG_F32_VX == 2
+template <> struct Vec<float> {
+    static constexpr int N = 2;
+    typedef float2 T;
+    static __device__ __forceinline__ void unpack(const T &v, float *o) { o[0] = v.x; o[1] = v.y; }
+    static __device__ __forceinline__ T pack(const float *o) { return make_float2(o[0], o[1]); }
+    static __device__ __forceinline__ T zero() { return make_float2(0.f, 0.f); }
+    static __device__ __forceinline__ void lds(uint32_t addr, float *o)
+    {
+        asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(o[0]), "=f"(o[1]) : "r"(addr));
+    }
+    static __device__ __forceinline__ void sts(uint32_t addr, const float *o)
+    {
+        asm volatile("st.shared.v2.f32 [%0], {%1, %2};" ::"r"(addr), "f"(o[0]), "f"(o[1]) : "memory");
+    }
+};
+#else
 template <> struct Vec<float> {
     static constexpr int N = 4;
     typedef float4 T;
@@ -161,6 +189,7 @@ template <> struct Vec<float> {
         asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "f"(o[0]), "f"(o[1]), "f"(o[2]), "f"(o[3]) : "memory");
     }
 };
+#endif
 template <> struct Vec<double> {
     static constexpr int N = 2;
     typedef double2 T;
@@ -181,7 +210,9 @@ template <typename R, int S, bool RES, int TX, int TY> struct Stream3DCfg {
     static constexpr int VX = Vec<R>::N;
     static constexpr int NST = S + (RES ? 1 : 0);
     static constexpr int H = NST;
-    static constexpr int HX = (H + VX - 1) / VX * VX;
+    // x halo rounded to 16 bytes: the TMA box stays 16-byte aligned and (4-byte reals) 64 wide whatever VX is
+    static constexpr int HXQ = (VX * (int)sizeof(R) >= 16) ? VX : 16 / (int)sizeof(R);
+    static constexpr int HX = (H + HXQ - 1) / HXQ * HXQ;
     static constexpr int HY = RES ? (H + 1) / 2 * 2 : H;
     static constexpr int WX = TX + 2 * HX, WY = TY + 2 * HY;
     static constexpr int UX = WX / VX, UY = WY / 2;
@@ -212,7 +243,7 @@ template <typename R> struct Stream3DArgs {
     const R *Vp;      // PRO: coarse correction Vs[L/2]
     R *Rout;          // RES: Rs[L/2]
     int L;            // level width
-    int flags;        // debug: bit 0 = never take the steady-state body, bit 1 = always mask
+    int flags;        // debug: bit 0 = never take the steady-state body, bit 1 = always mask, bit 2 = always re-run chunks guarded
     // slab view (multi-GPU): the arrays hold planes [0, nplanes) of which [nz_lo, nz_hi) are
     // owned (written) by this rank; the global grid occupies local planes [zdom0, zdom1).
     // Single GPU: nz_lo = zdom0 = 0, nz_hi = zdom1 = L, rz_off = vz_off = 0.
@@ -231,6 +262,12 @@ template <typename R> struct Stream3DArgs {
     // neighbour has published, [48] CTAs of the current pass that are done}; hs_lo / hs_hi = the
     // neighbours' headers (null at the ends of the chain, and everywhere when hs is null).
     unsigned long long *hs, *hs_lo, *hs_hi;
+    // Lock-step partition (0 = balanced shares): the first ntiles CTAs take one whole tile column each over the
+    // owned planes [nz_lo, nz_lo + zsplit) and march through z together, so the halo rows and the partly used
+    // sectors neighbouring tiles share are served by L2; the remaining CTAs share the planes above in equal parts.
+    int zsplit;
+    // S3_FAST / S3_RERUN: {flag "repeat this pass with the guarded code", CTA arrival counter} (zero between passes)
+    unsigned int *redo;
 };
 
 __device__ __forceinline__ unsigned long long s3_ld_acquire_sys(const unsigned long long *p)
@@ -244,11 +281,27 @@ __device__ __forceinline__ void s3_st_release_sys(unsigned long long *p, unsigne
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 
-template <typename R, typename A, int S, bool PRO, bool RES, int TX, int TY>
+// MODE: how the division guard of mg_math.cuh (a tiny but non-zero numerator needs IEEE division) is handled.
+//   S3_GUARDED  every stage tests its group of numerators and branches to IEEE division (all arithmetic types);
+//   S3_FAST     (fp32) Markstein sequence for every point, NO branch in the pipeline: the guard is only a sticky
+//               minimum over the numerators' keys; a launch that trips the threshold raises a.redo[0];
+//   S3_RERUN    (fp32) launched right behind the S3_FAST kernel with the same arguments: returns at once unless
+//               a.redo[0] is raised, else performs the whole pass again with the guarded code (src is never
+//               written: the passes ping-pong). Never happens on ordinary data; bit-identical either way.
+// The per-stage branch cost 10-20 % of a pass (ptxas does not move the next stage's shared-memory loads across it),
+// and keeping both code versions in ONE kernel made the register allocator spill in the fast one.
+// Multi-GPU handshake: the entry wait is done by S3_GUARDED / S3_FAST, the publication by S3_GUARDED / S3_RERUN.
+enum { S3_GUARDED = 0, S3_FAST = 1, S3_RERUN = 2 };
+
+template <typename R, typename A, int S, bool PRO, bool RES, int TX, int TY, int MODE = S3_GUARDED>
 __global__ void __launch_bounds__((Stream3DCfg<R, S, RES, TX, TY>::NTHREADS), (Stream3DCfg<R, S, RES, TX, TY>::MIN_CTAS))
 k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ CUtensorMap f_map,
            Stream3DArgs<R> a, Coef<A> cf)
 {
+    static_assert(MODE == S3_GUARDED || (kPackedF32 && std::is_same<A, float>::value && std::is_same<R, float>::value),
+                  "the branch-free division is implemented for fp32 arithmetic");
+    static_assert(MG_STREAM_SHFL || !PRO, "the register-path prolongation needs the shuffled x-neighbours");
+    constexpr bool GUARDED = MODE != S3_FAST;
     typedef Stream3DCfg<R, S, RES, TX, TY> C;
     typedef typename Vec<R>::T VT;
     constexpr int VX = C::VX, NST = C::NST, H = C::H, NP = 2 * VX, NSLOT = C::NSLOT, NF = C::NF;
@@ -275,7 +328,17 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
 
     // Before touching ghost planes (ours, by TMA; the neighbours', by peer stores): both
     // neighbours must have finished as many passes as we have. Every CTA checks for itself.
-    if (a.hs != nullptr) {
+    bool skip = false;   // S3_RERUN with nothing to redo
+    if (MODE == S3_RERUN) {
+        // every CTA reads the flag BEFORE it counts itself in; the last one in resets flag and counter for the next pass
+        int redo = 0;
+        if (threadIdx.x == 0) {
+            redo = (int)*reinterpret_cast<volatile unsigned int *>(a.redo);
+            __threadfence();
+            if (atomicAdd(a.redo + 1, 1u) == gridDim.x - 1) { a.redo[1] = 0u; a.redo[0] = 0u; }
+        }
+        skip = __syncthreads_or(redo) == 0;
+    } else if (a.hs != nullptr) {
         if (threadIdx.x == 0) {
             const unsigned long long n = s3_ld_acquire_sys(a.hs);
             if (a.hs_lo != nullptr) while (s3_ld_acquire_sys(a.hs + 16) < n) { }
@@ -286,6 +349,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
 
     // One chunk = tile (x0, y0) streamed through the owned planes [z0, z1). A CTA may process
     // several chunks (balanced persistent partition, see the end of the kernel).
+    unsigned int mall = 0xffffffffu;   // S3_FAST: sticky minimum of the numerator keys over the whole launch
     auto run_chunk = [&](const int x0, const int y0, const int z0, const int z1) {
     const int TZ = z1 - z0;
     const int zb = z0 - H;          // plane index of input step 0
@@ -348,38 +412,51 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         tma_load_3d(sbase + F0, &f_map, x0 - C::HX, y0 - C::HY, zb, mb_u + 8);
     }
 
-    // PRO: add prolong(V) to the own points of an arrived source slot, in place. The coarse
-    // values are fetched at the START of the step (fix_load) and applied at its end (fix_apply),
-    // so their global-memory latency hides behind the step's stage work.
-    R vpre[2][VX / 2 > 0 ? VX / 2 : 1];
-    bool vpre_on = false;
-    auto fix_load = [&](int t) {
-        vpre_on = false;
+    // PRO: stage 1 reads  src + prolong(V)  (expandResidual + addTo, cpu-raw.lua:65-73,83-85): the coarse values
+    // under the unit's two rows and the rows above and below are fetched at the START of the step and added, in
+    // registers, to what stage 1 loads from the source slot at the END of the step (stage 1 runs last). The four
+    // fine rows gy0-1 .. gy0+2 lie over three coarse rows when gy0 is even and over two when it is odd (gy0 has the
+    // parity of the y halo). Outside the grid the source is +0 (TMA zero fill) and V reads as +0: 0 + 0 = +0.
+    constexpr bool YODD = (C::HY & 1) != 0;
+    constexpr int NVR = YODD ? 2 : 3;                        // coarse rows fetched
+    constexpr int VS_UP = 0, VS_C0 = YODD ? 0 : 1, VS_C1 = 1, VS_DN = YODD ? 1 : 2;   // fine row -> fetched coarse row
+    R vq[NVR][VX / 2 > 0 ? VX / 2 : 1];
+    R vxl[2] = {(R)0, (R)0}, vxr[2] = {(R)0, (R)0};   // tiles that patch lanes 0 / 31 from shared memory: the coarse
+                                                      // values left / right of the unit, for its two rows
+    // offsets of the coarse rows inside a coarse plane and whether they exist (constant over the chunk)
+    int voff[NVR];
+    bool vin[NVR];
+#pragma unroll
+    for (int r = 0; r < NVR; ++r) {
+        const int gy = gy0 + (r == 0 ? -1 : (YODD ? 1 : (r == 1 ? 0 : 2)));
+        vin[r] = PRO && worker && xin && gy >= 0 && gy < L;
+        voff[r] = vin[r] ? (gx0 >> 1) + (L >> 1) * (gy >> 1) : 0;
+    }
+    auto v_load = [&](int t) {
         if (!PRO) return;
         const int p = zb + t;
-        if (p < zdom0 || p >= zdom1) return;                       // plane outside the grid stays 0
-        vpre_on = true;
-        const int pc = ((p - zdom0) >> 1) + a.vz_off;              // coarse plane (local index)
-        const int L2 = L >> 1;
+        const bool pin = p >= zdom0 && p < zdom1;
+        const int pc = pin ? ((p - zdom0) >> 1) + a.vz_off : 0;    // coarse plane (local index)
+        const R *vp = a.Vp + (size_t)(L >> 1) * (size_t)(L >> 1) * (size_t)pc;
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const bool in = r == 0 ? in0 : in1;
-            const size_t crow = (size_t)(gx0 >> 1) + (size_t)L2 * ((size_t)((gy0 + r) >> 1) + (size_t)L2 * (size_t)pc);
+        for (int r = 0; r < NVR; ++r) {
+            const bool in = pin && vin[r];
+            if (VX == 4 && sizeof(R) == 4) {       // the two coarse values of a row are one aligned 8-byte load
+                float2 v = make_float2(0.f, 0.f);
+                if (in) v = __ldg(reinterpret_cast<const float2 *>(vp + voff[r]));
+                vq[r][0] = (R)v.x; vq[r][VX / 2 - 1] = (R)v.y;
+            } else {
 #pragma unroll
-            for (int i = 0; i < VX / 2; ++i) vpre[r][i] = in ? a.Vp[crow + i] : (R)0;
+                for (int i = 0; i < VX / 2; ++i) vq[r][i] = in ? __ldg(vp + voff[r] + i) : (R)0;
+            }
         }
-    };
-    auto fix_apply = [&](uint32_t slot_off) {
-        if (!PRO || !vpre_on) return;
+        if (!C::EDGE_FREE) {
 #pragma unroll
-        for (int r = 0; r < 2; ++r) {
-            const bool in = r == 0 ? in0 : in1;
-            if (!in) continue;
-            R u[VX];
-            Vec<R>::lds(a0 + slot_off + r * ROWB, u);
-#pragma unroll
-            for (int i = 0; i < VX; ++i) u[i] = (R)Ar<A>::add((A)u[i], (A)vpre[r][i >> 1]);
-            Vec<R>::sts(a0 + slot_off + r * ROWB, u);
+            for (int r = 0; r < 2; ++r) {
+                const int k = r == 0 ? VS_C0 : VS_C1;
+                vxl[r] = (pin && vin[k] && lane == 0 && gx0 - 1 >= 0) ? __ldg(vp + voff[k] - 1) : (R)0;
+                vxr[r] = (pin && vin[k] && lane == 31 && gx0 + VX < L) ? __ldg(vp + voff[k] + VX / 2) : (R)0;
+            }
         }
     };
 
@@ -393,6 +470,8 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     // back from the shared-memory ring.
     // (fp32 arithmetic only: with 8-byte accumulators the extra registers would spill.)
     constexpr bool CARRY = MG_STREAM_CARRY && sizeof(A) == 4;
+    constexpr bool DEFER = CARRY && MG_STREAM_DEFER;
+    constexpr int EARLY = CARRY ? MG_STREAM_EARLY : 0;   // 0: none, 1: neighbour rows + shuffles, 2: also f
     R carry[CARRY && NST > 1 ? NST - 1 : 1][NP];
 #pragma unroll
     for (int s = 0; s < (CARRY && NST > 1 ? NST - 1 : 1); ++s)
@@ -401,13 +480,6 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     A rpart[VX / 2 > 0 ? VX / 2 : 1];  // RES: restriction partial sums of the even plane
 #pragma unroll
     for (int i = 0; i < VX / 2; ++i) rpart[i] = (A)0;
-
-    if (PRO) {
-        fix_load(0);
-        mbar_wait(mb_u, 0);
-        fix_apply(0);
-        __syncthreads();
-    }
 
     // ring cursors, advanced once per step (no integer division in the loop); bu / bfq are the
     // same cursors as byte offsets
@@ -428,19 +500,15 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                 const int j = t + 1;                          // f plane stage 1 needs at step t + 2
                 int ksf = sf + 2; if (ksf >= NF) ksf -= NF;   // (t + 1) % NF  (sf = (t - 1) % NF)
                 // The slots being refilled were last READ through the generic proxy before the barrier that ended
-                // step t-1 (the values are in registers). Only PRO also WROTE the source slot (fix_apply):
-                // order those writes before the async-proxy refill.
-                if (PRO) fence_proxy_async_smem();
+                // step t-1 (the values are in registers); nothing writes them through the generic proxy.
                 mbar_expect_tx(mb_u + 8 * ks, 2 * C::PLANE_BYTES);
                 tma_load_3d(sbase + ks * SB, &src_map, x0 - C::HX, y0 - C::HY, zb + k, mb_u + 8 * ks);
                 tma_load_3d(sbase + F0 + ksf * SB, &f_map, x0 - C::HX, y0 - C::HY, zb + j, mb_u + 8 * ks);
             }
         }
-        if (PRO && t + 1 < nin) fix_load(t + 1);
-        // (2) source plane of this step (PRO: it was awaited and fixed up during step t-1)
-        if (!PRO) {
-            if (ST || t < nin) mbar_wait(mb_u + 8 * su, (uint32_t)pu);
-        }
+        if (PRO && (ST || t < nin)) v_load(t);
+        // (2) source plane of this step
+        if (ST || t < nin) mbar_wait(mb_u + 8 * su, (uint32_t)pu);
         // (3) the pipeline stages. The stages of one step are independent of each other (each reads
         // what was written a step earlier), so they may run in any order, except that stage s+1 must
         // take its centre rows from the carry registers before stage s refills them.
@@ -450,9 +518,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         auto stage_emit = [&](int sidx) { return ST ? true : (t >= 3 * sidx + 2); };
         // everything stage sidx+1 reads this step: centre rows (source slot or carry), the rows above and
         // below from the plane stage sidx wrote into the ring a step ago, x-neighbours by shuffle, and f
-        auto load_inputs = [&](int sidx, bool emit, In &q) {
-            // input plane: this step's source slot, or the ring slot stage s-1 wrote during step t-1
-            const uint32_t ib = sidx == 0 ? bu : RING0 + (uint32_t)(2 * (sidx - 1) + ((t - 1) & 1)) * SB;
+        auto load_f = [&](int sidx, bool emit, In &q) {
             // f of the emitted plane, from the f ring (TMA zero fill covers everything outside the grid)
             if (emit) {
                 uint32_t fb = bfq - (uint32_t)(2 * sidx) * SB;     // slot (t - 1 - 2*sidx) % NF
@@ -463,6 +529,10 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
 #pragma unroll
                 for (int i = 0; i < NP; ++i) q.fv[i] = (R)0;
             }
+        };
+        auto load_nb = [&](int sidx, In &q) {
+            // input plane: this step's source slot, or the ring slot stage s-1 wrote during step t-1
+            const uint32_t ib = sidx == 0 ? bu : RING0 + (uint32_t)(2 * (sidx - 1) + ((t - 1) & 1)) * SB;
             if (sidx == 0 || !CARRY) {
                 Vec<R>::lds(a0 + ib, q.c0);
                 Vec<R>::lds(a0 + ib + ROWB, q.c1);
@@ -472,6 +542,27 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
             }
             Vec<R>::lds(aU + ib, q.up);
             Vec<R>::lds(aD + ib, q.dn);
+            if (PRO && sidx == 0 && kPackedF32 && std::is_same<A, float>::value && std::is_same<R, float>::value) {
+#pragma unroll
+                for (int k = 0; k < VX / 2; ++k) {   // u + prolong(V) as packed adds (both points of a pair share the coarse value)
+                    const float2 vu = make_float2((float)vq[VS_UP][k], (float)vq[VS_UP][k]), v0 = make_float2((float)vq[VS_C0][k], (float)vq[VS_C0][k]);
+                    const float2 v1 = make_float2((float)vq[VS_C1][k], (float)vq[VS_C1][k]), vd = make_float2((float)vq[VS_DN][k], (float)vq[VS_DN][k]);
+                    const float2 tu = __fadd2_rn(make_float2((float)q.up[2 * k], (float)q.up[2 * k + 1]), vu);
+                    const float2 t0 = __fadd2_rn(make_float2((float)q.c0[2 * k], (float)q.c0[2 * k + 1]), v0);
+                    const float2 t1 = __fadd2_rn(make_float2((float)q.c1[2 * k], (float)q.c1[2 * k + 1]), v1);
+                    const float2 td = __fadd2_rn(make_float2((float)q.dn[2 * k], (float)q.dn[2 * k + 1]), vd);
+                    q.up[2 * k] = (R)tu.x; q.up[2 * k + 1] = (R)tu.y; q.c0[2 * k] = (R)t0.x; q.c0[2 * k + 1] = (R)t0.y;
+                    q.c1[2 * k] = (R)t1.x; q.c1[2 * k + 1] = (R)t1.y; q.dn[2 * k] = (R)td.x; q.dn[2 * k + 1] = (R)td.y;
+                }
+            } else if (PRO && sidx == 0) {   // u + prolong(V), rounded to storage like addTo (cpu-raw.lua:83-85)
+#pragma unroll
+                for (int i = 0; i < VX; ++i) {
+                    q.up[i] = (R)Ar<A>::add((A)q.up[i], (A)vq[VS_UP][i >> 1]);
+                    q.c0[i] = (R)Ar<A>::add((A)q.c0[i], (A)vq[VS_C0][i >> 1]);
+                    q.c1[i] = (R)Ar<A>::add((A)q.c1[i], (A)vq[VS_C1][i >> 1]);
+                    q.dn[i] = (R)Ar<A>::add((A)q.dn[i], (A)vq[VS_DN][i >> 1]);
+                }
+            }
             // x-neighbours across units come from the adjacent lane (warp shuffle) instead of a
             // 4-byte shared load at 16-byte stride (4-way bank conflict). Where the adjacent lane is a
             // different row (ux = 0 or UX-1) the value is garbage, exactly in the garbage zone of the
@@ -481,14 +572,22 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                 q.l0 = __shfl_up_sync(0xffffffffu, q.c0[VX - 1], 1); q.l1 = __shfl_up_sync(0xffffffffu, q.c1[VX - 1], 1);
                 q.r0 = __shfl_down_sync(0xffffffffu, q.c0[0], 1); q.r1 = __shfl_down_sync(0xffffffffu, q.c1[0], 1);
                 if (!C::EDGE_FREE) {
-                    q.l0 = lds_if(lane == 0, aL + ib, q.l0); q.l1 = lds_if(lane == 0, aL + ib + ROWB, q.l1);
-                    q.r0 = lds_if(lane == 31, aR + ib, q.r0); q.r1 = lds_if(lane == 31, aR + ib + ROWB, q.r1);
+                    if (PRO && sidx == 0) {   // the patched values come from the raw source slot: they need their + prolong(V) too
+                        const R pl0 = (R)Ar<A>::add((A)lds_if(lane == 0, aL + ib, (R)0), (A)vxl[0]), pl1 = (R)Ar<A>::add((A)lds_if(lane == 0, aL + ib + ROWB, (R)0), (A)vxl[1]);
+                        const R pr0 = (R)Ar<A>::add((A)lds_if(lane == 31, aR + ib, (R)0), (A)vxr[0]), pr1 = (R)Ar<A>::add((A)lds_if(lane == 31, aR + ib + ROWB, (R)0), (A)vxr[1]);
+                        q.l0 = lane == 0 ? pl0 : q.l0; q.l1 = lane == 0 ? pl1 : q.l1;
+                        q.r0 = lane == 31 ? pr0 : q.r0; q.r1 = lane == 31 ? pr1 : q.r1;
+                    } else {
+                        q.l0 = lds_if(lane == 0, aL + ib, q.l0); q.l1 = lds_if(lane == 0, aL + ib + ROWB, q.l1);
+                        q.r0 = lds_if(lane == 31, aR + ib, q.r0); q.r1 = lds_if(lane == 31, aR + ib + ROWB, q.r1);
+                    }
                 }
             } else {
                 q.l0 = lds1(aL + ib, (R)0); q.l1 = lds1(aL + ib + ROWB, (R)0);
                 q.r0 = lds1(aR + ib, (R)0); q.r1 = lds1(aR + ib + ROWB, (R)0);
             }
         };
+        auto load_inputs = [&](int sidx, bool emit, In &q) { load_f(sidx, emit, q); load_nb(sidx, q); };
         // what a Jacobi stage does with its new plane o[]: masks, carry + ring for the next stage, or (last
         // sweep) the global store, plus the neighbours' ghost planes
         auto emit_jacobi = [&](int sidx, const A *o) {
@@ -505,7 +604,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
 #pragma unroll
                     for (int i = 0; i < NP; ++i) carry[sidx < NST - 1 ? sidx : 0][i] = outv[i];
                 }
-                if (worker) {
+                if (worker && !DEFER) {
                     const uint32_t ob = RING0 + (uint32_t)(2 * sidx + (t & 1)) * SB;
                     Vec<R>::sts(a0 + ob, outv);
                     Vec<R>::sts(a0 + ob + ROWB, outv + VX);
@@ -576,26 +675,46 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
             auto P = [](float a, float b) { return make_float2(a, b); };
             const float2 INV = P(cf.inv_h2, cf.inv_h2), NINV = P(-cf.inv_h2, -cf.inv_h2), AD = P(cf.adiag, cf.adiag);
             const float2 NAD = P(cf.nadiag, cf.nadiag), Y = P(cf.yneg, cf.yneg), M1 = P(-1.f, -1.f);
+            In qbuf[2];   // EARLY: double buffered stage inputs
+            auto load_early = [&](int sidx, In &q) {
+                if (EARLY >= 2) load_f(sidx, stage_emit(sidx), q);
+                load_nb(sidx, q);
+            };
+            if (EARLY && stage_active(NST - 1)) load_early(NST - 1, qbuf[0]);
 #pragma unroll
             for (int srev = 0; srev < NST; ++srev) {
                 const int sidx = NST - 1 - srev;
-                if (!stage_active(sidx)) continue;
+                if (!stage_active(sidx)) {
+                    if (EARLY && sidx > 0 && stage_active(sidx - 1)) load_early(sidx - 1, qbuf[(srev + 1) & 1]);
+                    continue;
+                }
                 const bool emit = stage_emit(sidx);
                 const bool is_res = RES && sidx == NST - 1;
-                In q;
-                load_inputs(sidx, emit, q);
+                In &q = qbuf[srev & 1];
+                if (EARLY < 2) load_f(sidx, emit, q);
+                if (!EARLY) load_nb(sidx, q);
                 // xl + xr pairs operands one element apart, which would cost register moves to pair up:
-                // these four sums per row stay scalar and land directly in aligned pairs
-                float2 sxx[4];
-                sxx[0] = P(__fadd_rn(q.l0, q.c0[1]), __fadd_rn(q.c0[0], q.c0[2])); sxx[1] = P(__fadd_rn(q.c0[1], q.c0[3]), __fadd_rn(q.c0[2], q.r0));
-                sxx[2] = P(__fadd_rn(q.l1, q.c1[1]), __fadd_rn(q.c1[0], q.c1[2])); sxx[3] = P(__fadd_rn(q.c1[1], q.c1[3]), __fadd_rn(q.c1[2], q.r1));
-                const float2 Cc[4] = {P(q.c0[0], q.c0[1]), P(q.c0[2], q.c0[3]), P(q.c1[0], q.c1[1]), P(q.c1[2], q.c1[3])};
-                const float2 YL[4] = {P(q.up[0], q.up[1]), P(q.up[2], q.up[3]), Cc[0], Cc[1]};
-                const float2 YR[4] = {Cc[2], Cc[3], P(q.dn[0], q.dn[1]), P(q.dn[2], q.dn[3])};
-                float2 T[4], F[4];
+                // these sums stay scalar and land directly in aligned pairs
+                constexpr int NPK = NP / 2, HPK = VX / 2;     // pairs per unit, pairs per row
+                float2 sxx[NPK], Cc[NPK], YL[NPK], YR[NPK];
+#pragma unroll
+                for (int k = 0; k < HPK; ++k) {
+                    const float a0l = k == 0 ? q.l0 : q.c0[2 * k - 1], a0r = k == HPK - 1 ? q.r0 : q.c0[2 * k + 2];
+                    const float a1l = k == 0 ? q.l1 : q.c1[2 * k - 1], a1r = k == HPK - 1 ? q.r1 : q.c1[2 * k + 2];
+                    sxx[k] = P(__fadd_rn(a0l, q.c0[2 * k + 1]), __fadd_rn(q.c0[2 * k], a0r));
+                    sxx[HPK + k] = P(__fadd_rn(a1l, q.c1[2 * k + 1]), __fadd_rn(q.c1[2 * k], a1r));
+                    Cc[k] = P(q.c0[2 * k], q.c0[2 * k + 1]);
+                    Cc[HPK + k] = P(q.c1[2 * k], q.c1[2 * k + 1]);
+                }
+#pragma unroll
+                for (int k = 0; k < HPK; ++k) {
+                    YL[k] = P(q.up[2 * k], q.up[2 * k + 1]); YL[HPK + k] = Cc[k];
+                    YR[k] = Cc[HPK + k]; YR[HPK + k] = P(q.dn[2 * k], q.dn[2 * k + 1]);
+                }
+                float2 T[NPK], F[NPK];
                 float o[NP];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < NPK; ++k) {
                     const float2 part = __fadd2_rn(__fadd2_rn(sxx[k], YL[k]), YR[k]);
                     const float2 PRV = P(prev[sidx][2 * k], prev[sidx][2 * k + 1]);
                     T[k] = __fadd2_rn(P(acc[sidx][2 * k], acc[sidx][2 * k + 1]), Cc[k]);   // pending plane gets its z+1
@@ -609,21 +728,27 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                     acc[sidx][2 * k] = NA.x; acc[sidx][2 * k + 1] = NA.y;
                     prev[sidx][2 * k] = Cc[k].x; prev[sidx][2 * k + 1] = Cc[k].y;
                 }
+                // the next stage's inputs do not depend on anything this step produces: request them now, so that
+                // their shared-memory / shuffle latency runs under this stage's division
+                if (EARLY && sidx > 0 && stage_active(sidx - 1)) load_early(sidx - 1, qbuf[(srev + 1) & 1]);
                 if (!emit) continue;
                 if (is_res) { emit_res(o); continue; }
-                float2 N[4];
+                float2 N[NPK];
 #pragma unroll
-                for (int k = 0; k < 4; ++k) N[k] = __ffma2_rn(T[k], NINV, F[k]);           // RN(f - S/h^2)
+                for (int k = 0; k < NPK; ++k) N[k] = __ffma2_rn(T[k], NINV, F[k]);         // RN(f - S/h^2)
                 // Division guard (mg_math.cuh): the Markstein sequence is exact unless a numerator is tiny
                 // but non-zero; one integer min-chain per group (the key ranks exact zeros highest), IEEE
                 // division for the group otherwise. (A floating-point pre-test of min |n| with FMNMX3 was
                 // measured 10 % slower per V-cycle.)
                 unsigned int m = 0xffffffffu;
+#ifndef MG_STREAM_NOGUARD
 #pragma unroll
-                for (int k = 0; k < 4; ++k) m = min(m, min(Ar<float>::guard_key(N[k].x), Ar<float>::guard_key(N[k].y)));
+                for (int k = 0; k < NPK; ++k) m = min(m, min(Ar<float>::guard_key(N[k].x), Ar<float>::guard_key(N[k].y)));
+#endif
+                if (!GUARDED) { mall = min(mall, m); m = 0xffffffffu; }
                 if (m >= Ar<float>::guard_threshold()) {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < NPK; ++k) {
                         const float2 q1 = __fmul2_rn(N[k], Y);
                         const float2 rr = __ffma2_rn(NAD, q1, N[k]);
                         const float2 q2 = __ffma2_rn(rr, Y, q1);
@@ -631,7 +756,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                     }
                 } else {
 #pragma unroll
-                    for (int k = 0; k < 4; ++k) {
+                    for (int k = 0; k < NPK; ++k) {
                         o[2 * k] = Ar<float>::div(N[k].x, cf.adiag);
                         o[2 * k + 1] = Ar<float>::div(N[k].y, cf.adiag);
                     }
@@ -684,11 +809,14 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
             }
         }
 
-        // (PRO) prepare next step's source plane in place
-        if (PRO && t + 1 < nin) {
-            const int sn = su + 1 == NSLOT ? 0 : su + 1;
-            mbar_wait(mb_u + 8 * sn, (uint32_t)(sn == 0 ? pu ^ 1 : pu));
-            fix_apply((uint32_t)sn * SB);
+        if (DEFER && worker) {
+#pragma unroll
+            for (int sidx = 0; sidx < NST - 1; ++sidx)
+                if (stage_active(sidx) && stage_emit(sidx)) {
+                    const uint32_t ob = RING0 + (uint32_t)(2 * sidx + (t & 1)) * SB;
+                    Vec<R>::sts(a0 + ob, carry[sidx]);
+                    Vec<R>::sts(a0 + ob + ROWB, carry[sidx] + VX);
+                }
         }
         __syncthreads();
         // advance the ring cursors
@@ -705,6 +833,11 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     const int t_lo = 3 * NST - 1;
     int t_hi = min(nin - 1, zdom1 - zb);   // stage 1 emits plane zb + t - 1 <= zdom1 - 1
     if ((a.flags & 1) || t_hi < t_lo) t_hi = t_lo - 1;            // no steady phase
+    if (MODE == S3_RERUN) {   // the (rare) guarded re-run: one compact copy of the generic body
+#pragma unroll 1
+        for (int t = 0; t < T; ++t) step(std::false_type{}, std::true_type{}, t);
+        return;
+    }
 #pragma unroll 1
     for (int phase = 0; phase < 3; ++phase) {
         if (phase == 1) {
@@ -726,23 +859,34 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     // Balanced persistent partition: the launch is ntiles x (owned planes / 2) plane pairs of
     // work, dealt out in equal contiguous shares to the gridDim.x CTAs (one per SM). A share
     // may end one tile column and begin the next; each piece is a chunk with its own halo.
+    // With zsplit > 0 the first ntiles CTAs take whole columns of the planes below the split
+    // (lock step), and only the planes above it are dealt out like that, to the other CTAs.
     {
-        const int ntx = (L + TX - 1) / TX, nty = (L + TY - 1) / TY;
-        const long long npair = (a.nz_hi - a.nz_lo) >> 1;
-        const long long W2 = (long long)ntx * nty * npair;
-        long long lo = W2 * blockIdx.x / gridDim.x;
-        const long long hi = W2 * (blockIdx.x + 1) / gridDim.x;
+        const int ntx = (L + TX - 1) / TX, nty = (L + TY - 1) / TY, ntiles = ntx * nty;
+        int zbase = a.nz_lo, nb = (int)gridDim.x, b = (int)blockIdx.x;
+        long long npair = (a.nz_hi - a.nz_lo) >> 1, lo, hi;
+        if (a.zsplit > 0 && b < ntiles) {           // one whole column below the split
+            npair = a.zsplit >> 1;
+            lo = npair * b; hi = lo + npair;
+        } else {
+            if (a.zsplit > 0) { zbase += a.zsplit; npair -= a.zsplit >> 1; b -= ntiles; nb -= ntiles; }
+            const long long W2 = (long long)ntiles * npair;
+            lo = W2 * b / nb; hi = W2 * (b + 1) / nb;
+        }
         while (lo < hi) {
             const long long tile = lo / npair, zp = lo - tile * npair;
             const long long n = min(npair - zp, hi - lo);
-            run_chunk((int)(tile % ntx) * TX, (int)(tile / ntx) * TY, a.nz_lo + 2 * (int)zp, a.nz_lo + 2 * (int)(zp + n));
+            if (!skip) run_chunk((int)(tile % ntx) * TX, (int)(tile / ntx) * TY, zbase + 2 * (int)zp, zbase + 2 * (int)(zp + n));
             lo += n;
         }
     }
 
     // The last CTA of the pass publishes "pass n+1 done" to both neighbours: all our stores,
     // local and into their ghost planes, are ordered before it.
-    if (a.hs != nullptr) {
+    if (MODE == S3_FAST) {   // flags bit 2 (debug): always ask for the guarded re-run
+        const bool bad = mall < Ar<float>::guard_threshold() || (a.flags & 4);
+        if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) atomicOr(a.redo, 1u);
+    } else if (a.hs != nullptr) {
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence_system();

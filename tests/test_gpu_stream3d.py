@@ -81,3 +81,41 @@ def test_point_source_boundary_interaction(solvers, orc, real):
         du, df = to_dev(u), to_dev(f)
         s.inPlaceIterativeSolver(L, du, df, h, 12)
         assert_bits_equal(to_host(du), ref_sweeps(orc, k, u, f, h, 12), f"boundary S={S}")
+
+
+@pytest.mark.parametrize("flags", [0, 4])
+def test_branch_free_division_and_guarded_rerun(solvers, orc, flags):
+    """fp32: the pass is the branch-free kernel (Markstein division everywhere, sticky guard) followed by the
+    guarded re-run kernel. flags = 4 forces the re-run of every pass; tiny but non-zero numerators (where the
+    Markstein sequence is NOT exact) must trip the sticky guard by themselves. Bit for bit either way."""
+    s = solvers("float")
+    k = orc.REAL_NAMES["float"]
+    L, h = 128, 1.0 / 128
+    s.set_option("fast_min_L", 64)
+    s.set_option("stream_flags", flags)
+    rng = np.random.default_rng(7)
+    try:
+        for scale in (1.0, 1e-33, 1e-38):
+            u = (rand_field(rng, 3, L, s.dtype).astype(np.float64) * scale).astype(s.dtype)
+            f = (rand_field(rng, 3, L, s.dtype).astype(np.float64) * scale * L * L).astype(s.dtype)
+            V = (rand_field(rng, 3, L // 2, s.dtype).astype(np.float64) * scale).astype(s.dtype)
+            u[::3, ::5, ::7] = 0          # exact zeros stay on the fast path
+            for S in (3, 4):
+                s.set_option("tb", S)
+                du, df = to_dev(u), to_dev(f)
+                s.inPlaceIterativeSolver(L, du, df, h, S)
+                assert_bits_equal(to_host(du), ref_sweeps(orc, k, u, f, h, S), f"plain S={S} scale={scale} flags={flags}")
+                du, dV = to_dev(u), to_dev(V)
+                s.prolong_add_smooth(L, du, df, h, S, dV)
+                w = ref_sweeps(orc, k, orc.add_to(k, u, orc.prolong(3, k, V)), f, h, S)
+                assert_bits_equal(to_host(du), w, f"PRO S={S} scale={scale} flags={flags}")
+            du, dR = to_dev(u), to_dev(np.zeros_like(V))
+            s.set_option("tb", 4)
+            s.smooth_residual_restrict(L, du, df, h, 7, dR)
+            w = ref_sweeps(orc, k, u, f, h, 7)
+            assert_bits_equal(to_host(du), w, f"RES u scale={scale} flags={flags}")
+            assert_bits_equal(to_host(dR), orc.restrict(3, k, orc.residual(3, k, f, w, h, 8)), f"RES R scale={scale} flags={flags}")
+    finally:
+        s.set_option("stream_flags", 0)
+        s.set_option("fast_min_L", 256)
+        s.set_option("tb", 4)
