@@ -126,6 +126,8 @@ def lib():
         "mg_nccl_unique_id": (i, [vp, sz]),
         "mg_create_slab": (i, [i, i, i, i, i, i, i, vp, sz, C.POINTER(vp)]),
         "mg_create_slab_local": (i, [i, i, i, i, i, i, C.POINTER(vp)]),
+        "mg_create_slab_multi": (i, [i, i, i, i, i, pi, C.POINTER(vp)]),
+        "mg_set_global_option": (i, [C.c_char_p, i]),
         "mg_slab_ipc_export": (i, [vp, vp, sz]),
         "mg_slab_ipc_attach": (i, [vp, vp, sz]),
         "mg_slab_info": (i, [vp, pi, pi, pi, pi, C.POINTER(u64), C.POINTER(u64)]),
@@ -215,11 +217,13 @@ class MultigridCUDA:
     max_cycles = 2      # cpu-raw.lua:245 `for iter=1,2`
 
     def __init__(self, size, real=None, cpuDepth=None, dim=2, device=-1, smooth=None, out=None,
-                 local_slabs=1, slab=None):
+                 local_slabs=1, slab=None, devices=None):
         """local_slabs > 1: cut the 3-D grid into that many slabs inside this process on one GPU
         (exercises the multi-GPU schedule on a single device; the object still looks like one
-        solver on the global grid). slab = (rank, nranks, nccl_id_bytes): this process's slab of
-        a multi-process solver (see `create_distributed`); buffers then hold the owned planes."""
+        solver on the global grid). devices = [0, 1, ...]: one slab per listed GPU, all driven by
+        this process (mg_create_slab_multi; what a single LuaJIT host would use). slab = (rank,
+        nranks, nccl_id_bytes): this process's slab of a multi-process solver (see
+        `create_distributed`); buffers then hold the owned planes."""
         self.real = real or "double"
         self.real_kind = REAL_NAMES[self.real] if isinstance(self.real, str) else int(self.real)
         self.dtype = np_dtype(self.real_kind)
@@ -234,6 +238,9 @@ class MultigridCUDA:
             idbuf = C.create_string_buffer(bytes(nid), len(nid))
             rc = lib().mg_create_slab(self.dim, self.size, self.real_kind, self.smooth, device, self.slab_rank,
                                       self.slab_n, idbuf, len(nid), C.byref(h))
+        elif devices is not None and len(devices) > 1:
+            arr = (C.c_int * len(devices))(*[int(d) for d in devices])
+            rc = lib().mg_create_slab_multi(self.dim, self.size, self.real_kind, self.smooth, len(devices), arr, C.byref(h))
         elif local_slabs > 1:
             rc = lib().mg_create_slab_local(self.dim, self.size, self.real_kind, self.smooth, device,
                                             int(local_slabs), C.byref(h))
@@ -516,15 +523,19 @@ def slab_partition(size, nranks):
     return levels
 
 
-def plan_passes(n, tb, has_res):
+def plan_passes(n, tb, has_res, extra_pass=False):
     """Host mirror of EngineT::plan_passes (csrc/mg_engine.cuh): how n Jacobi sweeps are split
-    into smoother passes of <= tb sweeps; with a fused residual stage the last pass has <= 3."""
+    into smoother passes of <= tb sweeps; with a fused residual stage the last pass has <= 3.
+    extra_pass: one pass more than necessary (the slab schedule keeps the pass count of a level
+    visit even, so that the ping-pong ends in u without a copy)."""
     plan, rem, last = [], n, 0
     if has_res:
         last = min(n, 3, tb)
         rem = n - last
     if rem > 0:
         k = (rem + tb - 1) // tb
+        if extra_pass and k < rem:
+            k += 1
         base, extra = divmod(rem, k)
         plan += [base + (1 if i < extra else 0) for i in range(k)]
     if has_res:
@@ -544,6 +555,9 @@ def slab_schedule(size, nranks, smooth=7, tb=4):
             return
         coarse = [x for x in slab_partition(size, nranks) if x["L"] == L // 2][0]
         pre = plan_passes(smooth, tb, True)
+        post = plan_passes(smooth, tb, False)
+        if (len(pre) + len(post)) % 2:          # keep the ping-pong even: the result must land in u by itself
+            post = plan_passes(smooth, tb, False, extra_pass=True)
         for i, s in enumerate(pre):
             res = i == len(pre) - 1
             ops.append(("exchange_u", L, s + (1 if res else 0)))
@@ -552,7 +566,7 @@ def slab_schedule(size, nranks, smooth=7, tb=4):
         visit(L // 2)
         if coarse["distributed"]:
             ops.append(("exchange_V", L // 2, 2))
-        for i, s in enumerate(plan_passes(smooth, tb, False)):
+        for i, s in enumerate(post):
             ops.append(("exchange_u", L, s))
             ops.append(("pass", L, dict(sweeps=s, res=False, pro=i == 0)))
 

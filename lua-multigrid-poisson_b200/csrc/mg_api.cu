@@ -20,6 +20,7 @@
 using namespace mg;
 
 static thread_local std::string g_create_error;
+int g_slab_min_planes = 32;   // "slab_min_planes" (mg_set_global_option), read by mg_ctx::init
 
 extern "C" {
 
@@ -57,6 +58,18 @@ static int create_common(int dim, int size, int real_kind, int smooth, int devic
     return MG_OK;
 }
 
+int mg_set_global_option(const char *name, int value)
+{
+    if (!name) return MG_EINVAL;
+    if (std::string(name) == "slab_min_planes") {
+        if (value < 8) { g_create_error = "slab_min_planes must be >= 8 (two ghost depths)"; return MG_EINVAL; }
+        g_slab_min_planes = value;
+        return MG_OK;
+    }
+    g_create_error = "mg_set_global_option: unknown option";
+    return MG_EINVAL;
+}
+
 int mg_create(int dim, int size, int real_kind, int smooth, int device, mg_ctx **out)
 {
     return create_common(dim, size, real_kind, smooth, device, 0, 1, out);
@@ -86,6 +99,8 @@ int mg_set_mode(mg_ctx *ctx, int mode)
 int mg_set_stream(mg_ctx *ctx, void *cuda_stream)
 {
     CTX_OR_FAIL(ctx);
+    if (ctx->group && !ctx->group->nccl && cuda_stream)
+        return ctx->fail(MG_EUNSUPPORTED, "mg_set_stream: a slab group in one process runs on its own stream(s)");
     ctx->stream = cuda_stream ? (cudaStream_t)cuda_stream : ctx->own_stream;
     ctx->borrowed_stream = cuda_stream != nullptr;
     return MG_OK;
@@ -160,8 +175,10 @@ int mg_init_cells(mg_ctx *ctx)
     CTX_OR_FAIL(ctx);
     int rc = MG_OK;
     if (ctx->group && !ctx->group->nccl) {
-        for (mg_ctx *m : ctx->group->m)
+        for (mg_ctx *m : ctx->group->m) {
+            if ((rc = m->activate())) return rc;
             if ((rc = m->eng->init_cells(m))) return rc;
+        }
     } else if ((rc = ctx->eng->init_cells(ctx))) {
         return rc;
     }
@@ -171,9 +188,11 @@ int mg_init_cells(mg_ctx *ctx)
 int mg_zero_corrections(mg_ctx *ctx)
 {
     CTX_OR_FAIL(ctx);
-    for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx}))
+    for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) {
+        if (int rc = m->activate()) return rc;
         for (int lv = 0; lv < m->nlevels; ++lv)
-            if (m->V[lv]) MG_CK(ctx, cudaMemsetAsync(m->V[lv], 0, m->level_bytes(lv), ctx->stream));
+            if (m->V[lv]) MG_CK(ctx, cudaMemsetAsync(m->V[lv], 0, m->level_bytes(lv), m->stream));
+    }
     return ctx->sync();
 }
 
@@ -557,6 +576,66 @@ int mg_create_slab_local(int dim, int size, int real_kind, int smooth, int devic
         mg_ctx *c = g->m[r];
         c->peer_lo = r > 0 ? (char *)g->m[r - 1]->arena : nullptr;
         c->peer_hi = r < nslabs - 1 ? (char *)g->m[r + 1]->arena : nullptr;
+        for (int o = 0; o < nslabs; ++o) c->peer[o] = (char *)g->m[o]->arena;
+        c->p2p = true;
+    }
+    *out = g->m[0];
+    return MG_OK;
+}
+
+// One process, one GPU per slab (the reference's host is a single LuaJIT process, test/test.lua:53-56): the slabs of
+// the group live on `ndev` different devices, each with its own stream; kernels, fused halo stores and handshakes are
+// those of the one-process-per-GPU transport, peer pointers come from cudaDeviceEnablePeerAccess.
+int mg_create_slab_multi(int dim, int size, int real_kind, int smooth, int ndev, const int *devices, mg_ctx **out)
+{
+    if (!out) return MG_EINVAL;
+    *out = nullptr;
+    if (ndev == 1) return create_common(dim, size, real_kind, smooth, devices ? devices[0] : 0, 0, 1, out);
+    if (ndev < 1 || ndev > S3_MAX_RANKS) { g_create_error = "mg_create_slab_multi: 1, 2, 4 or 8 devices"; return MG_EINVAL; }
+    int have = 0;
+    if (cudaGetDeviceCount(&have) != cudaSuccess || have < 1) { g_create_error = "no CUDA device: libmgpoisson has no CPU fallback"; return MG_ECUDA; }
+    std::vector<int> dev(ndev);
+    for (int r = 0; r < ndev; ++r) {
+        dev[r] = devices ? devices[r] : r;
+        if (dev[r] < 0 || dev[r] >= have) { g_create_error = "mg_create_slab_multi: no such device"; return MG_EINVAL; }
+        for (int o = 0; o < r; ++o)
+            if (dev[o] == dev[r]) { g_create_error = "mg_create_slab_multi: one slab per device (mg_create_slab_local puts several on one)"; return MG_EINVAL; }
+    }
+    for (int r = 0; r < ndev; ++r)
+        for (int o = 0; o < ndev; ++o) {
+            if (o == r) continue;
+            int can = 0;
+            if (cudaDeviceCanAccessPeer(&can, dev[r], dev[o]) != cudaSuccess || !can) {
+                g_create_error = "mg_create_slab_multi: the devices cannot access each other's memory (no NVLink / P2P)";
+                return MG_EUNSUPPORTED;
+            }
+            cudaSetDevice(dev[r]);
+            cudaError_t e = cudaDeviceEnablePeerAccess(dev[o], 0);
+            if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) {
+                g_create_error = std::string("cudaDeviceEnablePeerAccess: ") + cudaGetErrorString(e);
+                return MG_ECUDA;
+            }
+            cudaGetLastError();
+        }
+    SlabGroup *g = new SlabGroup();
+    g->nranks = ndev; g->multi = true;
+    for (int r = 0; r < ndev; ++r) {
+        mg_ctx *c = nullptr;
+        int rc = create_common(dim, size, real_kind, smooth, dev[r], r, ndev, &c);
+        if (rc) {
+            for (mg_ctx *m : g->m) { m->group = nullptr; m->release(); delete m; }
+            delete g;
+            return rc;
+        }
+        c->group = g;
+        g->m.push_back(c);
+    }
+    g->m[0]->owns_group = true;
+    for (int r = 0; r < ndev; ++r) {
+        mg_ctx *c = g->m[r];
+        c->peer_lo = r > 0 ? (char *)g->m[r - 1]->arena : nullptr;
+        c->peer_hi = r < ndev - 1 ? (char *)g->m[r + 1]->arena : nullptr;
+        for (int o = 0; o < ndev; ++o) c->peer[o] = (char *)g->m[o]->arena;
         c->p2p = true;
     }
     *out = g->m[0];
@@ -583,14 +662,15 @@ int mg_slab_ipc_attach(mg_ctx *ctx, const void *handles, size_t bytes)
     if (!ctx->group || !ctx->group->nccl) return ctx->fail(MG_ESTATE, "mg_slab_ipc_attach: not a multi-process slab");
     if (!handles || bytes < (size_t)ctx->nranks * sizeof(cudaIpcMemHandle_t)) return ctx->fail(MG_EINVAL, "mg_slab_ipc_attach: short buffer");
     const cudaIpcMemHandle_t *h = (const cudaIpcMemHandle_t *)handles;
-    if (ctx->rank > 0) {
-        cudaIpcMemHandle_t hh; memcpy(&hh, &h[ctx->rank - 1], sizeof(hh));
-        MG_CK(ctx, cudaIpcOpenMemHandle((void **)&ctx->peer_lo, hh, cudaIpcMemLazyEnablePeerAccess));
+    // every rank's arena, not only the neighbours': the RES pass of the last distributed level stores the restricted
+    // residual into every rank's copy of the first replicated level, and the all-gather epochs go to every header
+    for (int r = 0; r < ctx->nranks; ++r) {
+        if (r == ctx->rank) { ctx->peer[r] = (char *)ctx->arena; continue; }
+        cudaIpcMemHandle_t hh; memcpy(&hh, &h[r], sizeof(hh));
+        MG_CK(ctx, cudaIpcOpenMemHandle((void **)&ctx->peer[r], hh, cudaIpcMemLazyEnablePeerAccess));
     }
-    if (ctx->rank < ctx->nranks - 1) {
-        cudaIpcMemHandle_t hh; memcpy(&hh, &h[ctx->rank + 1], sizeof(hh));
-        MG_CK(ctx, cudaIpcOpenMemHandle((void **)&ctx->peer_hi, hh, cudaIpcMemLazyEnablePeerAccess));
-    }
+    ctx->peer_lo = ctx->rank > 0 ? ctx->peer[ctx->rank - 1] : nullptr;
+    ctx->peer_hi = ctx->rank < ctx->nranks - 1 ? ctx->peer[ctx->rank + 1] : nullptr;
     ctx->peer_ipc = true;
     ctx->p2p = true;
     ctx->u_ghost_dirty = ctx->f_ghost_dirty = true;

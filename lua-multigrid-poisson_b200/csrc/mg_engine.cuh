@@ -71,6 +71,8 @@ struct Engine;
         if (e_ != cudaSuccess) return (ctx)->fail_cuda(e_, #call);   \
     } while (0)
 
+extern int g_slab_min_planes;   // mg_api.cu
+
 struct mg_ctx {
     int dim = 0, size = 0, real_kind = 0, smooth = 7, device = 0, nlevels = 0, rank = 0, nranks = 1;
     size_t elem = 0, N = 0;
@@ -133,7 +135,8 @@ struct mg_ctx {
     // fused halo exchange over peer memory: the neighbours' arenas (same layout as ours), mapped
     // with CUDA IPC (other process) or simply their pointers (same process). p2p = use them.
     char *peer_lo = nullptr, *peer_hi = nullptr;
-    bool peer_ipc = false, p2p = false, slab_graph_opt = false;
+    char *peer[mg::S3_MAX_RANKS] = {};   // every rank's arena as seen from this rank (peer[rank] = arena); null = not mapped
+    bool peer_ipc = false, p2p = false, slab_graph_opt = true;
     size_t Ntop = 0;                    // elements allocated for a top-level field (incl. ghosts)
 
     int planes(int lv) const { return dist[lv] ? nzl[lv] + 2 * G : (dim == 3 ? (1 << lv) : 1); }
@@ -160,11 +163,8 @@ struct mg_ctx {
         if (cudaGetDevice(&cur) != cudaSuccess || cur != device) MG_CK(this, cudaSetDevice(device));
         return MG_OK;
     }
-    int sync()
-    {
-        MG_CK(this, cudaStreamSynchronize(stream));
-        return MG_OK;
-    }
+    int sync();          // this handle's stream (MULTI groups: every slab's), then the peer time-out words
+    int check_peers();
     void count_launch(int n = 1)
     {
         if (!capturing) launches += (uint64_t)n;
@@ -362,6 +362,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
     int launch_stream3d_t(mg_ctx *c, int lv, R *dst, const R *src, const R *f, const R *Vp, R *Rout, const Coef<A> &cf)
     {
         const int L = 1 << lv;
+        if (int rc0 = c->activate()) return rc0;   // MULTI groups: every slab has its own device
         // In-plane tile. 4-byte reals: 56 x 40 (+ halo = 64 wide): 16 vectors per row and a 256-byte row
         // pitch, so a warp holds two whole rows of units: every quarter-warp of a 128-bit shared-memory
         // access stays inside one row (bank-conflict free) and lanes 0 / 31 sit on tile edges, where the
@@ -453,7 +454,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         dim3 grid((unsigned)ncta, 1, 1);
         Stream3DArgs<R> a{dst, Vp, Rout, L, c->stream_flags, nz_lo, nz_hi, zdom0, zdom0 + L, rz_off, vz_off,
                           nullptr, nullptr, nullptr, nullptr, c->G, nullptr, nullptr, nullptr, zsplit,
-                          (unsigned int *)((char *)c->arena + ARENA_REDO_OFF)};
+                          (unsigned int *)((char *)c->arena + ARENA_REDO_OFF), f};
         if (c->dist[lv] && c->p2p) {  // fused halo exchange: same offsets inside the neighbours' arenas
             const size_t doff = c->arena_off(dst);
             if (c->peer_lo) a.peer_lo = (R *)(c->peer_lo + doff);
@@ -463,7 +464,13 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
                 if (c->peer_lo) a.rpeer_lo = (R *)(c->peer_lo + roff);
                 if (c->peer_hi) a.rpeer_hi = (R *)(c->peer_hi + roff);
             }
-            if (c->group && c->group->nccl) {  // other processes: handshake inside the kernel
+            if (Rout && !c->dist[lv - 1]) {   // first replicated level: all-gather by the producing threads
+                const size_t roff = c->arena_off(Rout);
+                a.rall_n = c->nranks;
+                for (int r = 0; r < c->nranks; ++r)
+                    a.rall[r] = (r != c->rank && c->peer[r]) ? (R *)(c->peer[r] + roff) : nullptr;
+            }
+            if (c->group && c->group->concurrent()) {  // the slabs run at the same time: handshake inside the kernel
                 a.hs = (unsigned long long *)c->arena;
                 a.hs_lo = (unsigned long long *)c->peer_lo;
                 a.hs_hi = (unsigned long long *)c->peer_hi;
@@ -552,19 +559,54 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             int e2 = api->GroupEnd();
             if (e || e2) return c->fail(MG_ECUDA, api->GetErrorString(e ? e : e2));
         } else {
+            // LOCAL: one device, one stream. MULTI: every slab on its own device and stream -- the sources must be
+            // final before the copies and the ghosts in place before any neighbour's next kernel: group-wide syncs
+            // (this path only runs after initCells / an upload, or with the fused exchange switched off).
+            int rc;
+            if (g->multi && (rc = group_sync(g))) return rc;
             for (int r = 0; r < g->nranks; ++r) {
                 mg_ctx *c = g->m[r];
+                if ((rc = c->activate())) return rc;
                 if (r > 0)
                     MG_CK(c, cudaMemcpyAsync(at(c, off) + (size_t)(G - depth) * pb,
                                              at(g->m[r - 1], off) + (size_t)(G + nz - depth) * pb, nb,
-                                             cudaMemcpyDeviceToDevice, c0->stream));
+                                             cudaMemcpyDefault, c->stream));
                 if (r < g->nranks - 1)
                     MG_CK(c, cudaMemcpyAsync(at(c, off) + (size_t)(G + nz) * pb, at(g->m[r + 1], off) + (size_t)G * pb,
-                                             nb, cudaMemcpyDeviceToDevice, c0->stream));
+                                             nb, cudaMemcpyDefault, c->stream));
             }
+            if (g->multi && (rc = group_sync(g))) return rc;
         }
         g->exchanges++;
         g->exchanged_bytes += 2 * nb;
+        return MG_OK;
+    }
+    static int group_sync(SlabGroup *g)
+    {
+        for (mg_ctx *c : g->m) {
+            int rc = c->activate();
+            if (rc) return rc;
+            MG_CK(c, cudaStreamSynchronize(c->stream));
+        }
+        return MG_OK;
+    }
+    // fused transport: the RES pass has stored this rank's part of the coarse residual into every rank's cube;
+    // publish the epoch to everybody, then wait for everybody's (mg_slab.cuh)
+    int slab_allgather_fence(SlabGroup *g)
+    {
+        if (!g->concurrent()) return MG_OK;   // LOCAL: one stream orders everything
+        for (mg_ctx *c : g->m) {
+            int rc = c->activate();
+            if (rc) return rc;
+            SlabPeers sp;
+            memset(&sp, 0, sizeof(sp));
+            sp.nranks = c->nranks; sp.rank = c->rank;
+            for (int r = 0; r < c->nranks; ++r) sp.hs[r] = (unsigned long long *)c->peer[r];
+            k_slab_signal_all<<<1, 32, 0, c->stream>>>(sp);
+            MG_LAUNCH_CHECK(c);
+            k_slab_wait_all<<<1, 32, 0, c->stream>>>(sp);
+            MG_LAUNCH_CHECK(c);
+        }
         return MG_OK;
     }
     // replicated level lv: every rank has produced planes [r*L/P, (r+1)*L/P) of the cube
@@ -577,11 +619,16 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             int e = g->api->AllGather(b + (size_t)c0->rank * part, b, part, NcclApi::kInt8, g->comm, c0->stream);
             if (e) return c0->fail(MG_ECUDA, g->api->GetErrorString(e));
         } else {
-            for (int r = 0; r < g->nranks; ++r)
+            int rc;
+            if (g->multi && (rc = group_sync(g))) return rc;
+            for (int r = 0; r < g->nranks; ++r) {
+                if ((rc = g->m[r]->activate())) return rc;
                 for (int o = 0; o < g->nranks; ++o)
                     if (o != r)
                         MG_CK(c0, cudaMemcpyAsync(at(g->m[r], off) + (size_t)o * part, at(g->m[o], off) + (size_t)o * part,
-                                                  part, cudaMemcpyDeviceToDevice, c0->stream));
+                                                  part, cudaMemcpyDefault, g->m[r]->stream));
+            }
+            if (g->multi && (rc = group_sync(g))) return rc;
         }
         return MG_OK;
     }
@@ -590,33 +637,37 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         mg_ctx *c0 = g->m[0];
         int rc;
         if (!c0->dist[lv]) {  // replicated: every rank runs the ordinary single-GPU path
-            if (g->nccl && c0->use_graph && !c0->capturing && !c0->prof_on) {
-                // one process per GPU: replay the whole coarse sub-cycle (dozens of small launches,
-                // no communication inside) from its own CUDA graph
-                mg_ctx *c = c0;
-                if (!c->rep_gexec) {
-                    cudaStream_t saved = c->stream;
-                    MG_CK(c, cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
-                    c->stream = c->cap_stream; c->capturing = true;
-                    rc = twogrid_fused(c, h, at(c, u_off), at(c, f_off), lv);
-                    c->stream = saved; c->capturing = false;
-                    cudaError_t e = cudaStreamEndCapture(c->cap_stream, &c->rep_graph);
-                    if (rc || e != cudaSuccess) {
-                        if (c->rep_graph) cudaGraphDestroy(c->rep_graph);
-                        c->rep_graph = nullptr;
-                        return rc ? rc : c->fail_cuda(e, "cudaStreamEndCapture (replicated levels)");
+            if (g->concurrent() && c0->use_graph && !c0->capturing && !c0->prof_on) {
+                // eager slab cycle on concurrent slabs: replay the whole coarse sub-cycle (dozens of small launches,
+                // no communication inside) from a CUDA graph per slab
+                for (mg_ctx *c : g->m) {
+                    if ((rc = c->activate())) return rc;
+                    if (!c->rep_gexec) {
+                        cudaStream_t saved = c->stream;
+                        MG_CK(c, cudaStreamBeginCapture(c->cap_stream, cudaStreamCaptureModeThreadLocal));
+                        c->stream = c->cap_stream; c->capturing = true;
+                        rc = twogrid_fused(c, h, at(c, u_off), at(c, f_off), lv);
+                        c->stream = saved; c->capturing = false;
+                        cudaError_t e = cudaStreamEndCapture(c->cap_stream, &c->rep_graph);
+                        if (rc || e != cudaSuccess) {
+                            if (c->rep_graph) cudaGraphDestroy(c->rep_graph);
+                            c->rep_graph = nullptr;
+                            return rc ? rc : c->fail_cuda(e, "cudaStreamEndCapture (replicated levels)");
+                        }
+                        MG_CK(c, cudaGraphInstantiate(&c->rep_gexec, c->rep_graph, 0));
+                        size_t nn = 0;
+                        MG_CK(c, cudaGraphGetNodes(c->rep_graph, nullptr, &nn));
+                        c->rep_nodes = nn;
                     }
-                    MG_CK(c, cudaGraphInstantiate(&c->rep_gexec, c->rep_graph, 0));
-                    size_t nn = 0;
-                    MG_CK(c, cudaGraphGetNodes(c->rep_graph, nullptr, &nn));
-                    c->rep_nodes = nn;
+                    MG_CK(c, cudaGraphLaunch(c->rep_gexec, c->stream));
+                    c0->launches += c->rep_nodes;
                 }
-                MG_CK(c, cudaGraphLaunch(c->rep_gexec, c->stream));
-                c->launches += c->rep_nodes;
                 return MG_OK;
             }
-            for (mg_ctx *c : g->m)
+            for (mg_ctx *c : g->m) {
+                if ((rc = c->activate())) return rc;
                 if ((rc = twogrid_fused(c, h, at(c, u_off), at(c, f_off), lv))) return rc;
+            }
             return MG_OK;
         }
         if constexpr (DIM == 3) {
@@ -645,6 +696,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             }
             // the restricted residual is the next level's right-hand side
             if (c0->dist[lv - 1]) rc = slab_exchange(g, Rc_off, lv - 1, c0->G);
+            else if (c0->p2p) rc = slab_allgather_fence(g);   // the RES pass stored into every rank's cube
             else rc = slab_allgather(g, Rc_off, lv - 1);
             if (rc) return rc;
             if ((rc = slab_twogrid(g, 2 * h, Vc_off, Rc_off, lv - 1))) return rc;   // cpu-raw.lua:221-222
@@ -664,8 +716,9 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
                 // the ghosts refreshed by an explicit exchange before the next pass reads them
                 for (mg_ctx *c : g->m) {
                     const size_t o = c->own_off_elems(lv) * c->elem;
+                    if ((rc = c->activate())) return rc;
                     MG_CK(c, cudaMemcpyAsync(at(c, u_off) + o, at(c, cur) + o, c->own_elems(lv) * c->elem,
-                                             cudaMemcpyDeviceToDevice, c0->stream));
+                                             cudaMemcpyDeviceToDevice, c->stream));
                 }
                 if ((rc = slab_exchange(g, u_off, lv, c0->G, true))) return rc;
             }
@@ -885,7 +938,9 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             } else {
                 for (mg_ctx *m : g->m) {
                     double part;
-                    int rc = frob_partial_sum(m, &part);
+                    int rc = m->activate();
+                    if (rc) return rc;
+                    rc = frob_partial_sum(m, &part);
                     if (rc) return rc;
                     tot += part;
                 }
@@ -1018,13 +1073,13 @@ inline int mg_ctx::init(int dim_, int size_, int real_kind_, int smooth_, int de
         // a level is cut across the ranks while every rank keeps at least this many planes
         // (>= 8 = two ghost depths); thinner levels are replicated. 32 measured best on 8 GPUs
         // (1024^3: 1733 vs 1666 units/s with 8); MGPOISSON_SLAB_MIN_PLANES tunes it.
-        int min_planes = 32;
+        int min_planes = g_slab_min_planes;   // mg_set_global_option("slab_min_planes"); the environment overrides it
         if (const char *e = getenv("MGPOISSON_SLAB_MIN_PLANES")) min_planes = atoi(e) < 8 ? 8 : atoi(e);
         for (int lv = 0; lv < nlevels; ++lv) {
             const int L = 1 << lv;
             if (L >= 64 && L / nranks >= min_planes) { dist[lv] = true; nzl[lv] = L / nranks; }
         }
-        if (!dist[nlevels - 1]) return fail(MG_EINVAL, "grid too small to be cut into slabs (need size >= 64 and size/nranks >= 8)");
+        if (!dist[nlevels - 1]) return fail(MG_EINVAL, "grid too small to be cut into slabs (need size >= 64 and size/nranks >= slab_min_planes, 32 by default)");
         stream_min_L = 64;
         tb = 4;
     }
@@ -1096,16 +1151,17 @@ inline void mg_ctx::release()
 {
     if (device >= 0) cudaSetDevice(device);
     if (peer_ipc) {
-        if (peer_lo) cudaIpcCloseMemHandle(peer_lo);
-        if (peer_hi) cudaIpcCloseMemHandle(peer_hi);
-        peer_lo = peer_hi = nullptr;
+        for (int r = 0; r < mg::S3_MAX_RANKS; ++r)
+            if (peer[r] && r != rank) cudaIpcCloseMemHandle(peer[r]);
     }
+    for (int r = 0; r < mg::S3_MAX_RANKS; ++r) peer[r] = nullptr;
+    peer_lo = peer_hi = nullptr;
     if (group && owns_group) {
         mg::SlabGroup *g = group;
         if (own_stream) cudaStreamSynchronize(stream);
         for (size_t r = 1; r < g->m.size(); ++r) {  // LOCAL: the other slabs belong to rank 0's handle
             g->m[r]->group = nullptr;
-            g->m[r]->own_stream = nullptr;         // shared with rank 0
+            if (!g->multi) g->m[r]->own_stream = nullptr;   // LOCAL: shared with rank 0 (MULTI: every slab owns its own)
             g->m[r]->release();
             delete g->m[r];
         }
@@ -1251,11 +1307,16 @@ static inline int mg_copy_impl(mg_ctx *c, int which, int level, void *host, size
         for (size_t r = 0; r < c->group->m.size(); ++r) {
             mg_ctx *m = c->group->m[r];
             char *dev = (char *)m->arena + off;
+            if (int rc = m->activate()) return rc;
+            auto cpm = [&](void *d, void *h, size_t nb) -> cudaError_t {
+                return in ? cudaMemcpyAsync(d, h, nb, cudaMemcpyHostToDevice, m->stream)
+                          : cudaMemcpyAsync(h, d, nb, cudaMemcpyDeviceToHost, m->stream);
+            };
             if (c->dist[lv]) {
                 const size_t own = c->own_elems(lv) * c->elem;
-                MG_CK(c, cp(dev + c->own_off_elems(lv) * c->elem, (char *)host + r * own, own));
+                MG_CK(c, cpm(dev + c->own_off_elems(lv) * c->elem, (char *)host + r * own, own));
             } else if (in || r == 0) {
-                MG_CK(c, cp(dev, host, full));
+                MG_CK(c, cpm(dev, host, full));
             }
         }
     }
@@ -1264,8 +1325,7 @@ static inline int mg_copy_impl(mg_ctx *c, int which, int level, void *host, size
             if (which == MG_BUF_F) m->f_ghost_dirty = true;
             if (which == MG_BUF_PSI) m->u_ghost_dirty = true;
         }
-    MG_CK(c, cudaStreamSynchronize(c->stream));
-    return MG_OK;
+    return c->sync();
 }
 inline int mg_ctx::copy_in(int which, int lv, const void *host, size_t bytes)
 {
@@ -1283,6 +1343,33 @@ inline void mg_ctx::drop_graph()
     if (rep_gexec) cudaGraphExecDestroy(rep_gexec);
     if (rep_graph) cudaGraphDestroy(rep_graph);
     gexec = rep_gexec = nullptr; graph = rep_graph = nullptr; graph_nodes = rep_nodes = 0;
+}
+
+inline int mg_ctx::sync()
+{
+    if (group && group->multi) {
+        for (mg_ctx *m : group->m) {
+            if (m->activate() != MG_OK) return fail(MG_ECUDA, "cudaSetDevice failed");
+            MG_CK(this, cudaStreamSynchronize(m->stream));
+        }
+    } else {
+        MG_CK(this, cudaStreamSynchronize(stream));
+    }
+    return check_peers();
+}
+
+// A slab kernel that waited HS_TIMEOUT_NS for a neighbour gave up and raised the time-out word of its arena header
+// (mg_stream3d.cuh, s3_wait_counter): report it instead of handing back garbage silently.
+inline int mg_ctx::check_peers()
+{
+    if (!group || !group->concurrent()) return MG_OK;
+    for (mg_ctx *m : group->m) {
+        unsigned long long w = 0;
+        if (m->activate() != MG_OK) return fail(MG_ECUDA, "cudaSetDevice failed");
+        MG_CK(this, cudaMemcpy(&w, (const char *)m->arena + 8 * mg::HS_TIMEOUT, sizeof(w), cudaMemcpyDeviceToHost));
+        if (w != 0) return fail(MG_ESTATE, "slab handshake timed out: a neighbouring rank did not answer within 20 s");
+    }
+    return MG_OK;
 }
 
 // twoGrid(1/size, psi, f, size) (cpu-raw.lua:247)
@@ -1327,8 +1414,10 @@ inline int mg_ctx::vcycle()
 inline int mg_ctx::step(double *err_out)
 {
     if (group) {
-        for (mg_ctx *m : group->m)
-            MG_CK(this, cudaMemcpyAsync(m->psiOld, m->psi, Ntop * elem, cudaMemcpyDeviceToDevice, stream));
+        for (mg_ctx *m : group->m) {
+            if (int rc = m->activate()) return rc;
+            MG_CK(this, cudaMemcpyAsync(m->psiOld, m->psi, Ntop * elem, cudaMemcpyDeviceToDevice, m->stream));
+        }
     } else {
         MG_CK(this, cudaMemcpyAsync(psiOld, psi, Ntop * elem, cudaMemcpyDeviceToDevice, stream));
     }

@@ -23,6 +23,9 @@
 //           and the ghost refresh after initCells / an upload.
 //   NCCL  : (option slab_p2p = 0) ncclSend/ncclRecv of the halo planes before every pass.
 //           libnccl is dlopen()ed, so single-GPU users (LuaJIT) do not need it.
+//   MULTI : one process, one GPU per slab (mg_create_slab_multi): the same fused kernels and handshakes as FUSED, peer
+//           pointers through cudaDeviceEnablePeerAccess instead of CUDA IPC, cudaMemcpyPeerAsync for the ghost refresh
+//           and host-side sums instead of NCCL. This is how a single LuaJIT process drives 2, 4 or 8 GPUs.
 //   LOCAL : all slabs in one process on one device and one stream (peer pointers are plain
 //           pointers; slab_p2p = 0 uses cudaMemcpyAsync). This is how the slab index arithmetic
 //           and the fused stores are tested on a single GPU.
@@ -34,6 +37,8 @@
 
 #include <string>
 #include <vector>
+
+#include "mg_stream3d.cuh"
 
 struct mg_ctx;
 
@@ -91,10 +96,40 @@ struct NcclApi {
     }
 };
 
+// ---- all-gather epochs of the first replicated level (fused transport). The RES pass of the last distributed level
+// stores the restricted residual into every rank's copy of the coarse cube (Stream3DArgs::rall). Behind it, on the same
+// stream, k_slab_signal_all bumps this rank's epoch and publishes it in every peer's header; k_slab_wait_all, ahead of
+// the replicated sub-cycle, waits until every rank has published the current epoch. No NCCL call is left inside a
+// V-cycle, so the whole cycle can be one CUDA graph.
+struct SlabPeers {
+    unsigned long long *hs[S3_MAX_RANKS];   // every rank's arena header (this rank's own included)
+    int nranks, rank;
+};
+__global__ void k_slab_signal_all(SlabPeers p)
+{
+    unsigned long long *own = p.hs[p.rank];
+    const int r = (int)threadIdx.x;
+    __threadfence_system();
+    const unsigned long long e = own[HS_AG_EPOCH] + 1;   // every thread reads before thread 0 writes (same warp, lock step)
+    __syncwarp();
+    if (r < p.nranks) s3_st_release_sys(p.hs[r] + HS_AG_FROM + p.rank, e);
+    __syncwarp();
+    if (r == 0) s3_st_release_sys(own + HS_AG_EPOCH, e);
+}
+__global__ void k_slab_wait_all(SlabPeers p)
+{
+    unsigned long long *own = p.hs[p.rank];
+    const int r = (int)threadIdx.x;
+    const unsigned long long e = s3_ld_acquire_sys(own + HS_AG_EPOCH);
+    if (r < p.nranks) s3_wait_counter(own + HS_AG_FROM + r, e, own);
+}
+
 struct SlabGroup {
-    std::vector<mg_ctx *> m;  // LOCAL: every rank's context; NCCL: this rank's only
+    std::vector<mg_ctx *> m;  // LOCAL / MULTI: every rank's context; NCCL: this rank's only
     int nranks = 1;
-    bool nccl = false;
+    bool nccl = false;        // one process per GPU: NCCL communicator for the ghost refresh after an upload and the reductions
+    bool multi = false;       // one process, one GPU per slab: peer copies and host-side sums instead
+    bool concurrent() const { return nccl || multi; }   // slabs run at the same time on different GPUs: in-kernel handshakes
     void *comm = nullptr;
     NcclApi *api = nullptr;
     uint64_t exchanges = 0, exchanged_bytes = 0;

@@ -69,6 +69,13 @@
 #define MG_STREAM_EARLY 0     // fp32: the next stage's inputs are requested before the current stage's division guard
                               // (1: neighbour rows + shuffles, 2: also its f rows)
 #endif
+#ifndef MG_F_TMEM
+#define MG_F_TMEM 0           // 4-byte reals: the f planes a thread needs live in TENSOR MEMORY (thread-private columns,
+                              // tcgen05.st / tcgen05.ld) instead of a shared-memory ring fed by TMA. MEASURED (round 2, 512^3
+                              // fp32, S = 4 pass): shared-memory wavefronts 97 M -> 68 M as intended, bit-identical, but
+                              // 0.47 -> 0.64 ms: an LDTM.x8 costs the SM ~16 cycles (64 B/clk) against 8 for the two LDS.128
+                              // it replaces, and it does not overlap them; requesting a stage ahead did not help. Off.
+#endif
 #ifndef MG_STEADY_UNROLL
 #define MG_STEADY_UNROLL 2    // unroll factor of the steady-state step loop
 #endif
@@ -127,6 +134,43 @@ __device__ __forceinline__ void tma_load_3d(uint32_t smem_dst, const CUtensorMap
         "l"(map), "r"(x), "r"(y), "r"(z), "r"(bar)
         : "memory");
 }
+
+// ---- tensor memory (TMEM) as thread-private storage: a warp owns the 32 lanes of its quarter (warp % 4), thread i of
+// the warp lane 32 * (warp % 4) + i; the .32x32b shape moves N consecutive 32-bit columns of that lane to / from N registers
+__device__ __forceinline__ void tmem_alloc(uint32_t smem_dst, uint32_t ncols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_dst), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_relinquish()
+{
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tmem_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, float *o)
+{
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]), "=f"(o[4]), "=f"(o[5]), "=f"(o[6]), "=f"(o[7]) : "r"(taddr));
+}
+// the loaded registers are only valid after this wait: they pass through it so that no use can be scheduled before it
+__device__ __forceinline__ void tmem_wait_ld8(float *o)
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+f"(o[0]), "+f"(o[1]), "+f"(o[2]), "+f"(o[3]), "+f"(o[4]), "+f"(o[5]), "+f"(o[6]), "+f"(o[7])::"memory");
+}
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const float *o)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "f"(o[0]), "f"(o[1]),
+                 "f"(o[2]), "f"(o[3]), "f"(o[4]), "f"(o[5]), "f"(o[6]), "f"(o[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_ld8(uint32_t, double *) {}
+__device__ __forceinline__ void tmem_wait_ld8(double *) {}
+__device__ __forceinline__ void tmem_st8(uint32_t, const double *) {}
 
 // predicated shared-memory load: returns *p if pred, else old (no branch, no access when !pred)
 __device__ __forceinline__ float lds_if(bool pred, uint32_t addr, float old)
@@ -206,6 +250,46 @@ template <> struct Vec<double> {
     }
 };
 
+constexpr int S3_MAX_RANKS = 8;
+// slab handshake words in the arena header (u64 indices): passes completed by this rank / published by the lower and
+// upper neighbour, CTAs done, all-gather epochs (mg_slab.cuh), peer time-out flag
+enum { HS_DONE = 0, HS_FROM_LO = 16, HS_FROM_HI = 32, HS_CTAS = 48, HS_AG_FROM = 72, HS_AG_EPOCH = 80, HS_TIMEOUT = 81 };
+constexpr unsigned long long HS_TIMEOUT_NS = 20ull * 1000 * 1000 * 1000;   // a neighbour that stays silent this long is dead
+
+__device__ __forceinline__ unsigned long long s3_globaltimer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ unsigned long long s3_ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void s3_st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+
+// spin until *p >= n (acquire, system scope). A peer that stays silent for HS_TIMEOUT_NS is taken for dead: the time-out
+// word of the own header is raised (the host reports MG_ESTATE at its next synchronisation) and the wait is given up.
+__device__ __forceinline__ void s3_wait_counter(const unsigned long long *p, unsigned long long n, unsigned long long *hs)
+{
+    if (p == nullptr) return;
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    while (s3_ld_acquire_sys(p) < n) {
+        if ((++spins & 1023u) == 0) {
+            const unsigned long long now = s3_globaltimer();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > HS_TIMEOUT_NS) { hs[HS_TIMEOUT] = 1ull; __threadfence_system(); return; }
+        }
+    }
+}
+
 template <typename R, int S, bool RES, int TX, int TY> struct Stream3DCfg {
     static constexpr int VX = Vec<R>::N;
     static constexpr int NST = S + (RES ? 1 : 0);
@@ -227,15 +311,21 @@ template <typename R, int S, bool RES, int TX, int TY> struct Stream3DCfg {
     static constexpr int SLOT_ELEMS = SLOT_BYTES / (int)sizeof(R);
     static constexpr int NSLOT = 3;         // source-plane ring (TMA prefetch distance NSLOT-1 = 2 steps, like f)
     static constexpr int NRING = NST - 1;   // intermediate stage outputs, double buffered
-    static constexpr int NF = 2 * NST + 1;  // f-plane ring: a plane lives 2*NST-1 steps, fetched 2 ahead
+    // f planes. 4-byte reals: in tensor memory, FTD planes of 2*VX columns per thread (a plane is stored at its own step
+    // and read by stage s 2s-1 steps later: 2*NST-1 steps of life, 8 is the next power of two), three warps share
+    // a lane quarter -> 3 * 64 = 192 of the 256 allocated columns. 8-byte reals: a shared-memory ring fed by TMA.
+    static constexpr bool FT = MG_F_TMEM && sizeof(R) == 4 && VX == 4;
+    static constexpr int FTD = 8, FT_COLS = 256;
+    static constexpr int NF = FT ? 0 : 2 * NST + 1;  // f-plane ring: a plane lives 2*NST-1 steps, fetched 2 ahead
     static constexpr int NSLOTS_TOTAL = NSLOT + 2 * NRING + NF;
-    static constexpr int SMEM_BYTES = NSLOTS_TOTAL * SLOT_BYTES + NSLOT * 8;   // slots + the source ring's mbarriers
+    static constexpr int SMEM_BYTES = NSLOTS_TOTAL * SLOT_BYTES + NSLOT * 8 + 16;   // slots + the source ring's mbarriers + TMEM base
     static_assert(NSLOT == 3, "source plane t+2 and f plane t+1 are fetched together and share an mbarrier");
     static_assert(TX % VX == 0 && TY % 2 == 0 && WY % 2 == 0, "tile shape");
     static_assert(NTHREADS <= 1024, "too many threads");
     static_assert(SMEM_BYTES <= 232448, "shared memory budget (227 KB)");
     // two CTAs per SM when the shared memory (plus the 1 KB the system reserves per CTA) allows it
-    static constexpr int MIN_CTAS = 2 * (SMEM_BYTES + 1024) <= 233472 && 2 * NTHREADS <= 1024 ? 2 : 1;
+    static constexpr int MIN_CTAS = !FT && 2 * (SMEM_BYTES + 1024) <= 233472 && 2 * NTHREADS <= 1024 ? 2 : 1;
+    static_assert(!FT || (NST <= 4 && (NTHREADS + 127) / 128 * 2 * VX * FTD <= FT_COLS), "tensor-memory budget of the f planes");
 };
 
 template <typename R> struct Stream3DArgs {
@@ -268,18 +358,12 @@ template <typename R> struct Stream3DArgs {
     int zsplit;
     // S3_FAST / S3_RERUN: {flag "repeat this pass with the guarded code", CTA arrival counter} (zero between passes)
     unsigned int *redo;
+    const R *fsrc;    // the right-hand side field itself (f planes in tensor memory are fetched by plain loads, not TMA)
+    // RES into a REPLICATED coarse level (multi-GPU): the restricted residual is also stored into every other rank's
+    // copy of the coarse cube -- the all-gather of the first replicated level, done by the producing threads.
+    R *rall[S3_MAX_RANKS];
+    int rall_n;
 };
-
-__device__ __forceinline__ unsigned long long s3_ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void s3_st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
 
 // MODE: how the division guard of mg_math.cuh (a tiny but non-zero numerator needs IEEE division) is handled.
 //   S3_GUARDED  every stage tests its group of numerators and branches to IEEE division (all arithmetic types);
@@ -340,11 +424,25 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         skip = __syncthreads_or(redo) == 0;
     } else if (a.hs != nullptr) {
         if (threadIdx.x == 0) {
-            const unsigned long long n = s3_ld_acquire_sys(a.hs);
-            if (a.hs_lo != nullptr) while (s3_ld_acquire_sys(a.hs + 16) < n) { }
-            if (a.hs_hi != nullptr) while (s3_ld_acquire_sys(a.hs + 32) < n) { }
+            const unsigned long long n = s3_ld_acquire_sys(a.hs + HS_DONE);
+            s3_wait_counter(a.hs_lo != nullptr ? a.hs + HS_FROM_LO : nullptr, n, a.hs);
+            s3_wait_counter(a.hs_hi != nullptr ? a.hs + HS_FROM_HI : nullptr, n, a.hs);
         }
         __syncthreads();
+    }
+
+    // f planes in tensor memory: warp 0 allocates FT_COLS columns for the CTA; every thread then owns 2*VX*FTD columns
+    // of its lane: lane 32 * (warp % 4) + laneid (implied by the warp), columns (warp / 4) * 64 onwards
+    constexpr bool FT = C::FT;
+    uint32_t tmem_base = 0, tf0 = 0;
+    if (FT && !skip) {
+        const uint32_t tslot = mb_u + NSLOT * 8;
+        if (tid < 32) { tmem_alloc(tslot, (uint32_t)C::FT_COLS); tmem_relinquish(); }
+        tmem_fence_before_sync();
+        __syncthreads();
+        tmem_fence_after_sync();
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(tmem_base) : "r"(tslot));
+        tf0 = tmem_base + ((uint32_t)((tid >> 5) & 3) << 21) + (uint32_t)((tid >> 7) * 2 * VX * C::FTD);
     }
 
     // One chunk = tile (x0, y0) streamed through the owned planes [z0, z1). A CTA may process
@@ -401,7 +499,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < NSLOT - 1; ++k)
             if (k < nin) {      // nin >= 4: planes 0 and 1 always exist
-                mbar_expect_tx(mb_u + 8 * k, k == 1 ? 2 * C::PLANE_BYTES : C::PLANE_BYTES);
+                mbar_expect_tx(mb_u + 8 * k, k == 1 && !FT ? 2 * C::PLANE_BYTES : C::PLANE_BYTES);
                 tma_load_3d(sbase + k * SB, &src_map, x0 - C::HX, y0 - C::HY, zb + k, mb_u + 8 * k);
             }
         // f plane j (global z = zb + j) is first needed at step j + 1 (stage 1) and last at step
@@ -409,8 +507,21 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         // the slot's previous tenant j - NF retired (step j - 2), and it is counted on that source
         // plane's mbarrier (awaited at step j + 1). Plane 0 is never used but is fetched here, with
         // source plane 1, so that every slot sees its planes in order.
-        tma_load_3d(sbase + F0, &f_map, x0 - C::HX, y0 - C::HY, zb, mb_u + 8);
+        if (!FT) tma_load_3d(sbase + F0, &f_map, x0 - C::HX, y0 - C::HY, zb, mb_u + 8);
     }
+    // (FT) f plane j is fetched with plain 128-bit loads at the top of step j, parked in tensor memory at its end,
+    // and read back by stage s at step j + 2s - 1
+    const R *fcur = reinterpret_cast<const R *>(reinterpret_cast<intptr_t>(a.fsrc) + (intptr_t)sizeof(R) *
+                    ((intptr_t)gx0 + (intptr_t)sL * (intptr_t)gy0 + (intptr_t)sLL * (intptr_t)zb));
+    R fnew[NP];
+    auto f_fetch = [&](int t, bool masked) {
+        const int p = zb + t;
+        const bool pin = p >= zdom0 && p < zdom1;     // f outside the grid is never used (those planes are masked to 0)
+        VT v0 = Vec<R>::zero(), v1 = Vec<R>::zero();
+        if (pin && (!masked || in0)) v0 = __ldg(reinterpret_cast<const VT *>(fcur));
+        if (pin && (!masked || in1)) v1 = __ldg(reinterpret_cast<const VT *>(fcur + sL));
+        Vec<R>::unpack(v0, fnew); Vec<R>::unpack(v1, fnew + VX);
+    };
 
     // PRO: stage 1 reads  src + prolong(V)  (expandResidual + addTo, cpu-raw.lua:65-73,83-85): the coarse values
     // under the unit's two rows and the rows above and below are fetched at the START of the step and added, in
@@ -501,12 +612,16 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                 int ksf = sf + 2; if (ksf >= NF) ksf -= NF;   // (t + 1) % NF  (sf = (t - 1) % NF)
                 // The slots being refilled were last READ through the generic proxy before the barrier that ended
                 // step t-1 (the values are in registers); nothing writes them through the generic proxy.
-                mbar_expect_tx(mb_u + 8 * ks, 2 * C::PLANE_BYTES);
+                mbar_expect_tx(mb_u + 8 * ks, FT ? C::PLANE_BYTES : 2 * C::PLANE_BYTES);
                 tma_load_3d(sbase + ks * SB, &src_map, x0 - C::HX, y0 - C::HY, zb + k, mb_u + 8 * ks);
-                tma_load_3d(sbase + F0 + ksf * SB, &f_map, x0 - C::HX, y0 - C::HY, zb + j, mb_u + 8 * ks);
+                if (!FT) tma_load_3d(sbase + F0 + ksf * SB, &f_map, x0 - C::HX, y0 - C::HY, zb + j, mb_u + 8 * ks);
             }
         }
         if (PRO && (ST || t < nin)) v_load(t);
+        if (FT) {
+            tmem_wait_st();                              // last step's plane is in tensor memory
+            if (ST || t < nin) f_fetch(t, MK);
+        }
         // (2) source plane of this step
         if (ST || t < nin) mbar_wait(mb_u + 8 * su, (uint32_t)pu);
         // (3) the pipeline stages. The stages of one step are independent of each other (each reads
@@ -520,7 +635,13 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         // below from the plane stage sidx wrote into the ring a step ago, x-neighbours by shuffle, and f
         auto load_f = [&](int sidx, bool emit, In &q) {
             // f of the emitted plane, from the f ring (TMA zero fill covers everything outside the grid)
-            if (emit) {
+            if (FT) {
+                if (emit) tmem_ld8(tf0 + (uint32_t)(((t - 1 - 2 * sidx) & (C::FTD - 1)) * 2 * VX), q.fv);
+                else {
+#pragma unroll
+                    for (int i = 0; i < NP; ++i) q.fv[i] = (R)0;
+                }
+            } else if (emit) {
                 uint32_t fb = bfq - (uint32_t)(2 * sidx) * SB;     // slot (t - 1 - 2*sidx) % NF
                 if ((int)fb < 0) fb += NF * SB;
                 Vec<R>::lds(a0 + F0 + fb, q.fv);
@@ -666,6 +787,8 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                     const int qc = (p - a.nz_lo) >> 1, nc = (a.nz_hi - a.nz_lo) >> 1;   // coarse owned index / count
                     if (a.rpeer_lo != nullptr && qc < a.ghost) a.rpeer_lo[cb + cidx + (size_t)L2 * L2 * (size_t)nc] = rv;
                     if (a.rpeer_hi != nullptr && qc >= nc - a.ghost) a.rpeer_hi[cb + cidx - (size_t)L2 * L2 * (size_t)nc] = rv;
+                    for (int r = 0; r < a.rall_n; ++r)          // replicated coarse level: same offset in every rank's cube
+                        if (a.rall[r] != nullptr) a.rall[r][cb + cidx] = rv;
                 }
             }
         };
@@ -711,22 +834,26 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                     YL[k] = P(q.up[2 * k], q.up[2 * k + 1]); YL[HPK + k] = Cc[k];
                     YR[k] = Cc[HPK + k]; YR[HPK + k] = P(q.dn[2 * k], q.dn[2 * k + 1]);
                 }
-                float2 T[NPK], F[NPK];
+                float2 T[NPK], F[NPK], AU[NPK];
                 float o[NP];
 #pragma unroll
                 for (int k = 0; k < NPK; ++k) {
                     const float2 part = __fadd2_rn(__fadd2_rn(sxx[k], YL[k]), YR[k]);
                     const float2 PRV = P(prev[sidx][2 * k], prev[sidx][2 * k + 1]);
                     T[k] = __fadd2_rn(P(acc[sidx][2 * k], acc[sidx][2 * k + 1]), Cc[k]);   // pending plane gets its z+1
-                    F[k] = P(q.fv[2 * k], q.fv[2 * k + 1]);
-                    if (is_res) {
-                        const float2 au = __fadd2_rn(__fmul2_rn(T[k], INV), __fmul2_rn(AD, PRV));
-                        const float2 rv = __ffma2_rn(au, M1, F[k]);                        // f - au
-                        o[2 * k] = rv.x; o[2 * k + 1] = rv.y;
-                    }
+                    if (is_res) AU[k] = __fadd2_rn(__fmul2_rn(T[k], INV), __fmul2_rn(AD, PRV));
                     const float2 NA = __fadd2_rn(part, PRV);                               // this plane gets its z-1
                     acc[sidx][2 * k] = NA.x; acc[sidx][2 * k + 1] = NA.y;
                     prev[sidx][2 * k] = Cc[k].x; prev[sidx][2 * k + 1] = Cc[k].y;
+                }
+                if (FT && emit) tmem_wait_ld8(q.fv);   // f of the emitted plane (tensor memory) has arrived
+#pragma unroll
+                for (int k = 0; k < NPK; ++k) {
+                    F[k] = P(q.fv[2 * k], q.fv[2 * k + 1]);
+                    if (is_res) {
+                        const float2 rv = __ffma2_rn(AU[k], M1, F[k]);                     // f - au
+                        o[2 * k] = rv.x; o[2 * k + 1] = rv.y;
+                    }
                 }
                 // the next stage's inputs do not depend on anything this step produces: request them now, so that
                 // their shared-memory / shuffle latency runs under this stage's division
@@ -773,6 +900,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                 const bool is_res = RES && sidx == NST - 1;
                 In q;
                 load_inputs(sidx, emit, q);
+                if (FT && emit) tmem_wait_ld8(q.fv);
                 A tot[NP], o[NP];
 #pragma unroll
                 for (int i = 0; i < VX; ++i) {
@@ -809,6 +937,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
             }
         }
 
+        if (FT && (ST || t < nin)) tmem_st8(tf0 + (uint32_t)((t & (C::FTD - 1)) * 2 * VX), fnew);
         if (DEFER && worker) {
 #pragma unroll
             for (int sidx = 0; sidx < NST - 1; ++sidx)
@@ -821,7 +950,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         __syncthreads();
         // advance the ring cursors
         bu += SB; bfq += SB;
-        dcur += sLL;
+        dcur += sLL; fcur += sLL;
         if (++su == NSLOT) { su = 0; bu = 0; pu ^= 1; }
         if (++sf == NF) { sf = 0; bfq = 0; }
     };
@@ -883,6 +1012,11 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
 
     // The last CTA of the pass publishes "pass n+1 done" to both neighbours: all our stores,
     // local and into their ghost planes, are ordered before it.
+    if (FT && !skip) {   // every tcgen05.ld was awaited by its consumer
+        tmem_fence_before_sync();
+        __syncthreads();
+        if (tid < 32) tmem_dealloc(tmem_base, (uint32_t)C::FT_COLS);
+    }
     if (MODE == S3_FAST) {   // flags bit 2 (debug): always ask for the guarded re-run
         const bool bad = mall < Ar<float>::guard_threshold() || (a.flags & 4);
         if (__syncthreads_or(bad ? 1 : 0) && threadIdx.x == 0) atomicOr(a.redo, 1u);
@@ -890,13 +1024,13 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         __syncthreads();
         if (threadIdx.x == 0) {
             __threadfence_system();
-            const unsigned int done = atomicAdd(reinterpret_cast<unsigned int *>(a.hs + 48), 1u);
+            const unsigned int done = atomicAdd(reinterpret_cast<unsigned int *>(a.hs + HS_CTAS), 1u);
             if (done == gridDim.x - 1) {
-                *reinterpret_cast<volatile unsigned int *>(a.hs + 48) = 0u;
-                const unsigned long long n = s3_ld_acquire_sys(a.hs) + 1;
-                s3_st_release_sys(a.hs, n);
-                if (a.hs_lo != nullptr) s3_st_release_sys(a.hs_lo + 32, n);   // we are its upper neighbour
-                if (a.hs_hi != nullptr) s3_st_release_sys(a.hs_hi + 16, n);   // and its lower neighbour
+                *reinterpret_cast<volatile unsigned int *>(a.hs + HS_CTAS) = 0u;
+                const unsigned long long n = s3_ld_acquire_sys(a.hs + HS_DONE) + 1;
+                s3_st_release_sys(a.hs + HS_DONE, n);
+                if (a.hs_lo != nullptr) s3_st_release_sys(a.hs_lo + HS_FROM_HI, n);   // we are its upper neighbour
+                if (a.hs_hi != nullptr) s3_st_release_sys(a.hs_hi + HS_FROM_LO, n);   // and its lower neighbour
             }
         }
     }

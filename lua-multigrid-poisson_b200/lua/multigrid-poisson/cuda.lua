@@ -157,11 +157,25 @@ int mg_nccl_unique_id(void *id, size_t bytes);
 int mg_create_slab(int dim, int size, int real_kind, int smooth, int device, int rank, int nranks,
                    const void *nccl_id, size_t id_bytes, mg_ctx **out);
 int mg_create_slab_local(int dim, int size, int real_kind, int smooth, int device, int nslabs, mg_ctx **out);
+/*  mg_create_slab_multi one process, one GPU per slab: what a single LuaJIT process (the reference's host,
+ *                       test/test.lua:53-56; gpu.lua:27-30 picks ONE device) uses to drive 2, 4 or 8 GPUs. devices =
+ *                       ndev device ordinals (NULL: 0 .. ndev-1), which must be able to access each other's memory.
+ *                       The handle behaves like a single solver on the global grid (upload / download / step take the
+ *                       whole field); kernels, fused halo stores and in-kernel handshakes are those of mg_create_slab. */
+int mg_create_slab_multi(int dim, int size, int real_kind, int smooth, int ndev, const int *devices, mg_ctx **out);
+/* process-wide defaults read by the next mg_create*: "slab_min_planes" (a level is cut across the ranks while every
+ * rank keeps at least this many planes, default 32, >= 8; thinner levels are replicated -- the `cpuDepth` idea of
+ * cpu-gpu.lua:11-15 at the scale of GPUs). The environment variable MGPOISSON_SLAB_MIN_PLANES still overrides it. */
+int mg_set_global_option(const char *name, int value);
 /* Fused halo exchange: every rank exports the CUDA IPC handle of its arena (64 bytes); after an
- * all-gather each rank attaches its two neighbours. From then on the smoother kernel that
- * produces a boundary plane stores it straight into the neighbour's ghost planes over NVLink,
- * and the only inter-GPU operation per pass is a flag handshake (option "slab_p2p" = 0 goes
- * back to ncclSend/ncclRecv). mg_create_slab_local uses the same path with plain pointers. */
+ * all-gather each rank attaches every other rank's arena. From then on the smoother kernel that
+ * produces a boundary plane stores it straight into the neighbour's ghost planes over NVLink, the
+ * kernel that restricts into the first replicated level stores into every rank's copy of it, and
+ * the only inter-GPU operations of a V-cycle are flag handshakes inside those kernels: no NCCL call
+ * is left in the cycle, which is replayed from one CUDA graph (option "slab_graph"). Option
+ * "slab_p2p" = 0 goes back to ncclSend/ncclRecv/ncclAllGather. mg_create_slab_local and
+ * mg_create_slab_multi use the same path with plain pointers. A rank whose neighbour stays silent
+ * for 20 s gives up; the next synchronising call then returns MG_ESTATE. */
 int mg_slab_ipc_export(mg_ctx *ctx, void *handle, size_t bytes);
 int mg_slab_ipc_attach(mg_ctx *ctx, const void *handles, size_t bytes);
 int mg_slab_info(mg_ctx *ctx, int *rank, int *nranks, int *own_planes, int *ghost, uint64_t *exchanges,
