@@ -6,13 +6,24 @@ point-source problem of the reference (cpu-raw.lua:8-20). N=1 workload: 3-D 512^
 (BASELINE.json configs[2], the configuration the metric is quoted on).
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
-                  [--dim 3 --size 512 --real float] [--tb T --small-L S --no-graph]
+                  [--config c1|c2|c3|c5] [--dim 3 --size 512 --real float] [--tb T --small-L S --no-graph]
+
+--config picks a BASELINE.json configuration: c1 = configs[0] 2-D 64^2 fp64, c2 = configs[1] 2-D 4096^2 fp32,
+c3 = configs[2] 3-D 512^3 fp32 (default, the headline), c5 = configs[4] 2-D 2048^2 fp64 with the multigrid-vs-Krylov leg
+(`mg_vs_cg`); --gpus N > 1 is configs[3], the 1024^3 grid in z-slabs.
 
 Prints ONE JSON line (rank 0). Keys beyond the base contract:
-  roofline      dominant kernel: algorithmic (A_op) bytes per launch / CUDA-event duration
-  vcycle        whole V-cycle effective bandwidth against A_op
+  roofline      dominant kernel. `achieved` / `frac` = DRAM bytes the launch really moves (ncu dram__bytes, from
+                profiles/dram_traffic.json; the compulsory bytes of the fused launch when no capture exists) / CUDA-event
+                duration, against the measured copy peak: a true roofline fraction (<= ~1). The A_op figure of SURVEY
+                8(d) (bytes of the un-fused reference operators the launch replaces; temporal blocking pushes it above
+                the peak) is kept beside it as `effective_*`.
+  vcycle        whole V-cycle: A_op effective bandwidth, the fused lower bound A_min, DRAM bytes per cycle
   cpu_baseline  the CPU oracle (C restatement of cpu-raw.lua) timed on this host
   e2e           same metric through mg_step_host with pinned HOST buffers, copies timed
+  parity        (--gpus N > 1) before timing: one V-cycle at 256^3 and at the timed 1024^3 slab shape, every rank's
+                slab of psi / Rs[L/2] / Vs[L/2] compared (CRC-32 of the bytes) with a single-GPU solver on rank 0;
+                a mismatch ends the run with a non-zero exit code
 """
 import argparse
 import json
@@ -37,6 +48,14 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
+CONFIGS = {
+    "c1": dict(dim=2, size=64, real="double", name="configs[0] (2D 64x64 Poisson, the reference's own cpu-raw.lua case)"),
+    "c2": dict(dim=2, size=4096, real="float", name="configs[1] (2D 4096x4096 fp32 V-cycle on 1xB200)"),
+    "c3": dict(dim=3, size=512, real="float", name="configs[2] (3D 512^3 fp32 V-cycle on 1xB200)"),
+    "c5": dict(dim=2, size=2048, real="double", name="configs[4] (2D 2048x2048 fp64 multigrid-vs-Krylov convergence)"),
+}
+
+
 def level_sizes(dim, size):
     L, out = size, []
     while L >= 1:
@@ -57,6 +76,27 @@ def a_op_bytes(dim, size, elem, smooth=7):
         else:
             words += (2 * smooth * 3 + 3 + (1 + c) + (1 + c) + 3) * n
     return words * elem
+
+
+def a_min_bytes(dim, size, elem):
+    """Fused lower bound of one V-cycle (SURVEY 8(d) A_min): per level visit the pre-smoothing leg reads u, f and
+    writes u, R/2^dim; the post-smoothing leg reads u, f, V/2^dim and writes u: 6 + 2c words per point."""
+    c = 2.0 ** -dim
+    return sum((6 + 2 * c) * float(L) ** dim for L in level_sizes(dim, size) if L > 1) * elem + 3 * elem
+
+
+def compulsory_bytes(kind, dim, L, sweeps, elem):
+    """Bytes ONE fused launch cannot avoid: read u and f, write u (+ read V or write R, 2^-dim of a field)."""
+    c = 2.0 ** -dim
+    n = float(L) ** dim
+    if kind == "copy":
+        return 2 * n * elem
+    if kind == "small_levels":
+        return a_min_bytes(dim, L, elem)
+    w = 3.0
+    if kind in ("sweep+prolong_add", "sweep+residual_restrict", "prolong_add", "residual_restrict"):
+        w += c
+    return w * n * elem
 
 
 def launch_bytes(kind, dim, L, sweeps, elem):
@@ -168,8 +208,9 @@ def run_reference(args):
     except AttributeError:
         nthreads = os.cpu_count() or 1
     steps, warm = max(args.steps, 1), max(args.warmup, 0)
-    per_step_budget = min(20.0, 150.0 / (steps + warm))
-    # choose the sample cube once, then time exactly `steps` V-cycles on it
+    # the whole run (warm-up + timed steps) gets ~150 s: the unit workload at its REAL size when that fits,
+    # else the largest cube that does, with the rate scaled by the point count (the V-cycle is linear in N)
+    per_step_budget = 150.0 / (steps + warm)
     _, sample, _ = oracle_rate(args.dim, args.size, args.real, nthreads, per_step_budget)
     o = oracle.Oracle(sample, args.real, args.dim, nthreads=nthreads)
     for _ in range(warm):
@@ -181,19 +222,22 @@ def run_reference(args):
     o.close()
     scale = (float(sample) / args.size) ** args.dim
     value = steps / dt * scale
-    sample_txt = (f"{steps} V-cycles of the {args.dim}-D {sample}^{args.dim} {args.real} point-source problem, "
-                  f"rate scaled by ({sample}/{args.size})^{args.dim} to the {args.size}^{args.dim} workload")
+    extrapolated = sample != args.size
+    sample_txt = (f"{steps} V-cycles of the {args.dim}-D {sample}^{args.dim} {args.real} point-source problem on {nthreads} threads"
+                  + (f", rate scaled by ({sample}/{args.size})^{args.dim} to the {args.size}^{args.dim} unit workload (EXTRAPOLATED: "
+                     f"the full size does not fit the time budget)" if extrapolated else " (the unit workload at its real size)"))
+    world = max(1, args.gpus)
     line = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": "V-cycles/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warm, "ms_per_step": 1e3 / value, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": dtype_name(args.real),
-        "data": "synthetic", "config": dict(workload_config(args, 1), note=(
-            "the CPU path runs the unit workload on this one host whatever --gpus is; the GPU arm at --gpus N > 1 "
-            "runs the 1024^3 grid and reports the same unit (V-cycles of this workload per second)")),
+        "data": "synthetic", "config": workload_config(args, world),
         "cpu_baseline": {"value": value, "unit": "V-cycles/s", "cores": nthreads, "kind": "port",
-                         "sample": sample_txt},
+                         "sample": sample_txt, "extrapolated": extrapolated},
         "e2e": {"value": value, "unit": "V-cycles/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "note": "reference = C restatement of cpu-raw.lua (oracle port); LuaJIT is not available on this image",
+        "note": ("reference = C restatement of cpu-raw.lua (oracle port); LuaJIT is not available on this image. The CPU path runs "
+                 "the unit workload (one V-cycle of the N = 1 grid) on this one host whatever --gpus is; the GPU arm at --gpus N > 1 "
+                 "runs the 1024^3 grid and reports the same unit (V-cycles of the unit workload per second)"),
     }
     print(json.dumps(line))
 
@@ -204,21 +248,126 @@ def dtype_name(real):
 
 def l2_policy(args):
     mib = args.size ** args.dim * (8 if args.real == "double" else 4) / 2 ** 20
+    if 3 * mib > 126:
+        return ("inputs larger than L2: one smoother pass touches 3 top-level fields of %.0f MiB each (L2 is 126 MB); "
+                "no flush needed" % mib)
     if 4 * mib > 126:
-        return "inputs larger than L2 (each of the 4 top-level fields is %.0f MiB; L2 is 126 MB); no flush needed" % mib
+        return ("PARTLY L2 RESIDENT: the 4 top-level fields (%.0f MiB each) exceed the 126 MB L2 together, but one smoother pass "
+                "touches only 3 of them (%.0f MiB), which fit: not a clean HBM measurement" % (mib, 3 * mib))
     return ("working set (4 fields x %.2f MiB) FITS in the 126 MB L2: not an HBM measurement; this size is a parity/"
             "latency case, not the roofline workload" % mib)
 
 
+def baseline_config_name(args):
+    for c in CONFIGS.values():
+        if (c["dim"], c["size"], c["real"]) == (args.dim, args.size, args.real):
+            return c["name"]
+    return "custom"
+
+
 def workload_config(args, world):
+    """Pure function of the command line: both arms (--impl ours / reference) print the same dict."""
     size = args.size
-    return {
+    cfg = {
         "workload": f"{args.dim}D {size}^{args.dim} {dtype_name(args.real)} Poisson V-cycle, Dirichlet-0, point-source RHS, "
                     f"7+7 Jacobi(omega=1) sweeps per level, {len(level_sizes(args.dim, size))} levels",
-        "baseline_config": "configs[2] (3D 512^3 fp32 V-cycle on 1xB200)" if (args.dim, size, args.real) == (3, 512, "float") else "custom",
+        "baseline_config": baseline_config_name(args),
         "grid": [size] * args.dim, "parallelism": f"slab x{world}" if world > 1 else "single GPU",
         "l2_policy": l2_policy(args),
     }
+    if world > 1:
+        g = args.mgpu_size
+        unit_scale = (float(g) / size) ** args.dim
+        cfg.update({
+            "workload": f"{args.dim}D {g}^{args.dim} {dtype_name(args.real)} Poisson V-cycle cut into {world} z-slabs "
+                        f"({g // world} planes + 4 ghost planes per side per GPU); halo planes are stored into the neighbour's "
+                        f"ghost planes by the smoother kernel itself over NVLink peer memory (CUDA IPC), handshake inside the "
+                        f"kernel; levels with < 32 planes per GPU replicated, their right-hand side all-gathered by the "
+                        f"restricting kernel's peer stores; no NCCL call inside a V-cycle; the cycle is one CUDA graph per GPU",
+            "baseline_config": "configs[3] (3D 1024^3 fp32 slab-decomposed across 2/4/8 B200)",
+            "grid": [g] * args.dim, "parallelism": f"z-slabs x{world}",
+            "unit": f"value counts V-cycles of the N=1 workload ({size}^{args.dim}); one {g}^{args.dim} V-cycle = {unit_scale:g} units",
+            "points_per_gpu": g ** args.dim // world, "points_per_gpu_at_n1": size ** args.dim,
+            "scaling_note": (f"the grid is {g}^{args.dim} at every N > 1: N = {int(unit_scale)} holds the N = 1 points per GPU (weak), "
+                             f"smaller N hold {int(unit_scale)}/N times as many (read the 2 -> 4 -> 8 steps as strong scaling)"),
+            "l2_policy": "inputs larger than L2 (a slab's fields are >= 512 MiB each)",
+        })
+    return cfg
+
+
+def mg_vs_cg(pkg, args, budget_s=8.0, tol=1e-10):
+    """BASELINE config [4] (test/converge-multigrid-vs-krylov.lua): the multigrid the experiment drives (cpu.lua: coarse
+    corrections re-zeroed every cycle, cpu.lua:138) against conjugate gradient on the same operator with b = f, x0 = -f
+    (:38-69), both run towards a relative residual `tol`. The multigrid leg is bounded by `budget_s` (omega = 1 Jacobi leaves
+    the top mode nearly undamped: the cycle count grows ~3.7x per grid doubling)."""
+    s = pkg.MultigridCUDA(args.size, args.real, dim=args.dim, out=False)
+    r0 = s.residual_norm()
+    s.zero_corrections(); s.vcycle(); s.residual_norm()      # warm-up: graph capture
+    s.init_cells()
+    t0, c, r, check = time.perf_counter(), 0, r0, 200
+    while time.perf_counter() - t0 < budget_s:
+        for _ in range(check):
+            s.zero_corrections()
+            s.vcycle()
+        c += check
+        r = s.residual_norm()
+        if not (r > tol * r0):
+            break
+    mg = {"variant": "cpu.lua (mg_zero_corrections + mg_vcycle per cycle)", "cycles": c, "seconds": time.perf_counter() - t0,
+          "residual_rel": r / r0, "reached_tol": bool(r <= tol * r0), "linf_psi": s.linf_norm(), "budget_s": budget_s}
+    s.init_cells()
+    t0 = time.perf_counter()
+    errs, linf = s.conjgrad(max_iter=50000, epsilon=tol)
+    dt = time.perf_counter() - t0
+    cg = {"iterations": len(errs), "seconds": dt, "err_r_over_b": errs[-1] if errs else None,
+          "residual_rel": s.residual_norm() / r0, "reached_tol": bool(errs and errs[-1] < tol), "linf_x": linf[-1] if linf else None,
+          "parity": "unpinned: the reference's solver.conjgrad is an un-vendored dependency; checked against the oracle's textbook CG"}
+    s.close()
+    return {"tol": tol, "quantity": "multigrid: ||f - A psi|| / ||f - A psi_0||; CG: ||r|| / ||b|| (what solver.conjgrad tests)",
+            "multigrid": mg, "conjugate_gradient": cg}
+
+
+def slab_parity(pkg, torch, dist, size, args, rank, world, local, solver):
+    """One V-cycle (mg_step) on the slab solver and on a single-GPU solver of the same grid (rank 0); every rank's
+    planes of psi, Rs[size/2] and Vs[size/2] must agree byte for byte (CRC-32 per slab), `err` to 1e-9 relative."""
+    import zlib
+    import numpy as np
+    own = solver if solver is not None else pkg.create_distributed(size, args.real, dim=args.dim)
+    own.init_cells()
+    own.zero_corrections()
+    err = own.step()
+    half = size // 2
+    crcs = [zlib.crc32(np.ascontiguousarray(b.download()).tobytes()) for b in (own.psi, own.Rs[half], own.Vs[half])]
+    mine = torch.tensor(crcs + [0], dtype=torch.int64, device="cuda")
+    mine[3] = int(np.float64(err).view(np.int64))
+    allc = [torch.empty_like(mine) for _ in range(world)]
+    dist.all_gather(allc, mine)
+    ok = True
+    if rank == 0:
+        one = pkg.MultigridCUDA(size, args.real, dim=args.dim, device=local, out=False)
+        one.set_option("stream_min_L", 64)
+        ref_err = one.step()
+        nz = size // world
+        for name, buf, L in (("psi", one.psi, size), ("Rs", one.Rs[half], half), ("Vs", one.Vs[half], half)):
+            full = np.ascontiguousarray(buf.download())
+            idx = {"psi": 0, "Rs": 1, "Vs": 2}[name]
+            dist_level = (L // world) >= 32 and L >= 64      # the library's rule (slab_partition): else replicated
+            for r in range(world):
+                part = full[r * (L // world):(r + 1) * (L // world)] if dist_level else full
+                if zlib.crc32(part.tobytes()) != int(allc[r][idx].item()):
+                    ok = False
+                    print(f"[bench parity] {size}^3: {name} of rank {r} differs from the single-GPU solver", file=sys.stderr)
+        errs = [float(np.int64(int(c[3].item())).view(np.float64)) for c in allc]
+        if any(abs(e - ref_err) > 1e-9 * abs(ref_err) for e in errs):
+            ok = False
+            print(f"[bench parity] {size}^3: err {errs} vs single GPU {ref_err}", file=sys.stderr)
+        one.close()
+        del nz
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, 0)
+    if solver is None:
+        own.close()
+    return bool(int(flag.item()))
 
 
 def run_ours(args):
@@ -261,6 +410,22 @@ def run_ours(args):
     s.set_stream(stream.cuda_stream)
     lib, h = pkg.lib(), s._h
 
+    # ---- multi-GPU parity BEFORE timing: 256^3 and the timed slab shape against a single-GPU solver on rank 0
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = {}
+        for psize in sorted({256, gsize}):
+            ok = slab_parity(pkg, torch, dist, psize, args, rank, world, local, s if psize == gsize else None)
+            parity[str(psize)] = ok
+        if not all(parity.values()):
+            if rank == 0:
+                print(json.dumps({"metric": METRIC, "n_gpus": world, "parity": parity,
+                                  "error": "multi-GPU result differs from the single-GPU solver: no timing reported"}))
+            dist.destroy_process_group()
+            raise SystemExit(3)
+        s.init_cells()
+        s.zero_corrections()
+
     def barrier():
         if dist is not None:
             dist.barrier()
@@ -271,14 +436,16 @@ def run_ours(args):
         lib.mg_vcycle_async(h)
     # The reference's iteration (omega = 1 Jacobi, injection prolongation) DIVERGES after a few
     # cycles (its `err` grows ~16x every 5 cycles from cycle ~5 on, oracle/ and tests/golden), so the
-    # state is re-initialised after the warm-up to keep the timed fields finite; kernel time does
-    # not depend on the values.
+    # state is re-initialised after the warm-up to keep the timed fields finite. Kernel time does not depend
+    # on the values as long as they are ordinary: only a pass that meets a tiny (< 1e-20) non-zero numerator is
+    # run a second time by the guarded kernel (mg_stream3d.cuh), which does not happen on this problem.
     s.init_cells()
     s.zero_corrections()
     barrier()
     clocks = ClockSampler(local)
     clocks.start()
     n0 = s.launch_count()
+    tr0 = s.slab_traffic() if world > 1 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         e0.record()
@@ -290,10 +457,22 @@ def run_ours(args):
     ms = e0.elapsed_time(e1)
     clk = clocks.stop()
     launches = s.launch_count() - n0
+    nvl = None
     if dist is not None:
         t = torch.tensor([ms], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+        tr1 = s.slab_traffic()
+        per_step = (tr1["peer_store_bytes"] - tr0["peer_store_bytes"]) / args.steps
+        tb = torch.tensor([per_step], device="cuda", dtype=torch.float64)
+        dist.all_reduce(tb, op=dist.ReduceOp.SUM)
+        nvl = {"peer_store_bytes_per_step_this_rank": per_step, "peer_store_bytes_per_step_all_ranks": float(tb.item()),
+               "gbs_per_gpu_out": per_step / (ms / args.steps * 1e-3) / 1e9,
+               "explicit_exchange_bytes_in_timed_region": tr1["exchange_bytes"] - tr0["exchange_bytes"],
+               "peak_per_direction_gbs": 770.0,
+               "note": "bytes the smoother kernels store straight into other GPUs' memory (G = 4 boundary planes per neighbour "
+                       "and pass, coarse boundary planes, the fused all-gather), counted per launch from the planes sent; "
+                       "770 GB/s = measured peer-copy bandwidth per direction (B200_PROFILING.md)"}
     ms_per_step = ms / args.steps
     value = unit_scale * 1e3 / ms_per_step
     diverged = not bool(np.isfinite(s.step()))   # expected after enough cycles: the reference's iteration diverges
@@ -321,24 +500,47 @@ def run_ours(args):
     total_prof = sum(g["ms"] for g in groups.values())
     (dk, dL, dsw), dg = max(groups.items(), key=lambda kv: kv[1]["ms"])
     dom_ms = dg["ms"] / dg["n"]
-    dom_bytes = launch_bytes(dk, args.dim, dL, dsw, elem) / (world if dL >= 64 else 1)  # this rank's slab
-    achieved = dom_bytes / (dom_ms * 1e-3) / 1e9
+    share = (world if dL >= 64 and world > 1 else 1)          # this rank's slab of a distributed level
+    aop_launch = launch_bytes(dk, args.dim, dL, dsw, elem) / share
+    comp_launch = compulsory_bytes(dk, args.dim, dL, dsw, elem) / share
     kname = f"{dk}[L={dL},sweeps={dsw}]"
-    traffic = None
+    key = f"{args.dim}d_{gsize if world > 1 else args.size}_{args.real}" + (f"_n{world}" if world > 1 else "")
+    traffic_tab = {}
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(
-            f"{args.dim}d_{args.size}_{args.real}", {}).get(kname)
+        traffic_tab = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get(key, {})
     except Exception:
         pass
+    traffic = traffic_tab.get(kname)
+    moved = traffic if traffic else comp_launch
+    achieved = moved / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": kname, "launches_per_step": dg["n"],
-                "avg_launch_ms": dom_ms, "algorithmic_bytes_per_launch": dom_bytes,
+                "traffic": traffic, "kernel": kname, "launches_per_step": dg["n"], "avg_launch_ms": dom_ms,
+                "bytes_source": ("ncu dram__bytes_read.sum + dram__bytes_write.sum of this launch (profiles/dram_traffic.json)"
+                                 if traffic else "compulsory bytes of the fused launch (no ncu capture of this kernel at this size)"),
+                "compulsory_bytes_per_launch": comp_launch, "compulsory_gbs": comp_launch / (dom_ms * 1e-3) / 1e9,
+                "traffic_over_compulsory": (traffic / comp_launch) if traffic else None,
+                "effective_bytes_per_launch_A_op": aop_launch, "effective_gbs_A_op": aop_launch / (dom_ms * 1e-3) / 1e9,
+                "effective_frac_A_op": aop_launch / (dom_ms * 1e-3) / 1e9 / peak,
                 "share_of_step": dg["ms"] / total_prof, "peak_source": peak_src,
-                "frac_of_nominal_8000": achieved / NOMINAL_HBM_GBS}
+                "frac_of_nominal_8000": achieved / NOMINAL_HBM_GBS,
+                "note": "frac is DRAM bytes moved / time / measured copy peak; the A_op figure (SURVEY 8(d)) counts the bytes the "
+                        "un-fused reference operators would move and exceeds the peak by design of temporal blocking"}
     aop = a_op_bytes(args.dim, gsize, elem)
+    amin = a_min_bytes(args.dim, gsize, elem)
     v_gbs = aop / (ms_per_step * 1e-3) / 1e9 / world   # per GPU
-    vcycle = {"a_op_bytes": aop, "effective_gbs_per_gpu": v_gbs, "frac_of_measured": v_gbs / peak,
-              "frac_of_nominal_8000": v_gbs / NOMINAL_HBM_GBS,
+    cyc_traffic = None
+    if traffic_tab:   # DRAM bytes of a whole cycle where every stream/warp launch has a capture; the rest at compulsory bytes
+        cyc_traffic = 0.0
+        for (k, L, sw), g in groups.items():
+            t = traffic_tab.get(f"{k}[L={L},sweeps={sw}]")
+            cyc_traffic += g["n"] * (t if t else compulsory_bytes(k, args.dim, L, sw, elem) / (world if L >= 64 and world > 1 else 1))
+    vcycle = {"a_op_bytes": aop, "effective_gbs_per_gpu": v_gbs, "effective_frac_of_measured": v_gbs / peak,
+              "effective_frac_of_nominal_8000": v_gbs / NOMINAL_HBM_GBS,
+              "a_min_bytes": amin, "a_min_gbs_per_gpu": amin / (ms_per_step * 1e-3) / 1e9 / world,
+              "a_min_frac_of_measured": amin / (ms_per_step * 1e-3) / 1e9 / world / peak,
+              "dram_bytes_per_cycle_per_gpu": cyc_traffic,
+              "dram_gbs_per_gpu": (cyc_traffic / (ms_per_step * 1e-3) / 1e9) if cyc_traffic else None,
+              "dram_frac_of_measured": (cyc_traffic / (ms_per_step * 1e-3) / 1e9 / peak) if cyc_traffic else None,
               "breakdown_ms": {f"{k}[L={L},sweeps={sw}]x{g['n']}": round(g["ms"], 4)
                                for (k, L, sw), g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])[:8]},
               "profiled_sum_ms": total_prof}
@@ -398,6 +600,13 @@ def run_ours(args):
         except Exception as e:  # never let the extra figure break the bench line
             ttt = {"unavailable": repr(e)[:200]}
 
+    mgcg = None
+    if rank == 0 and world == 1 and (args.dim, args.size, args.real) == (2, 2048, "double"):
+        try:
+            mgcg = mg_vs_cg(pkg, args)
+        except Exception as e:
+            mgcg = {"unavailable": repr(e)[:200]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": "V-cycles/s", "n_gpus": world, "steps": args.steps,
@@ -406,22 +615,13 @@ def run_ours(args):
             "config": workload_config(args, world), "roofline": roofline, "vcycle": vcycle,
             "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": launches, "clocks": clk,
             "tuning": {"tb": args.tb, "small_L": args.small_L, "graph": not args.no_graph, "opt": args.opt},
-            "time_to_tolerance": ttt, "finite": finite, "err_cycles_1_to_4": first_errs,
+            "time_to_tolerance": ttt, "mg_vs_cg": mgcg, "finite": finite, "err_cycles_1_to_4": first_errs,
             "state_overflowed_during_timed_cycles": diverged,
             "note": "the reference's omega=1 V-cycle diverges after ~5 cycles (BASELINE.md 5.4); kernel time is value independent",
         }
         if world > 1:
-            si = s.slab_info()
-            line["config"].update({
-                "workload": f"{args.dim}D {gsize}^{args.dim} {dtype_name(args.real)} Poisson V-cycle cut into {world} z-slabs "
-                            f"({si['own_planes']} planes + {si['ghost']} ghost planes per side per GPU); halo planes are stored "
-                            f"into the neighbour's ghost planes by the smoother kernel itself over NVLink peer memory "
-                            f"(CUDA IPC), handshake inside the kernel; levels with < 32 planes per GPU replicated (NCCL all-gather)",
-                "baseline_config": "configs[3] (3D 1024^3 fp32 slab-decomposed across 2/4/8 B200)",
-                "grid": [gsize] * args.dim, "parallelism": f"z-slabs x{world}",
-                "unit": f"value counts V-cycles of the N=1 workload ({args.size}^{args.dim}); one {gsize}^{args.dim} V-cycle = {unit_scale:g} units",
-                "halo_exchanges_per_step": (si["exchanges"]) // max(1, args.steps + max(args.warmup, 3) + 5 + 1 + ne2e + 1),
-            })
+            line["parity"] = parity
+            line["nvlink"] = nvl
         print(json.dumps(line))
     s.close()
     if dist is not None:
@@ -434,16 +634,22 @@ def main():
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--dim", type=int, default=3)
-    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--dim", type=int, default=None)
+    ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--mgpu-size", dest="mgpu_size", type=int, default=1024, help="global grid width for --gpus > 1")
-    ap.add_argument("--real", default="float", choices=["float", "double", "float_acc64"])
+    ap.add_argument("--real", default=None, choices=["float", "double", "float_acc64"])
     ap.add_argument("--tb", type=int, default=-1)
     ap.add_argument("--small-L", dest="small_L", type=int, default=-1)
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-parity", dest="no_parity", action="store_true", help="skip the multi-GPU parity check before timing")
+    ap.add_argument("--config", default=None, choices=sorted(CONFIGS), help="a BASELINE.json configuration (default c3)")
     ap.add_argument("--opt", action="append", default=[], help="library option name=value (mg_set_option)")
     args = ap.parse_args()
+    preset = CONFIGS[args.config or "c3"]
+    for k in ("dim", "size", "real"):
+        if getattr(args, k) is None:
+            setattr(args, k, preset[k])
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -193,6 +193,9 @@ int mg_slab_ipc_export(mg_ctx *ctx, void *handle, size_t bytes);
 int mg_slab_ipc_attach(mg_ctx *ctx, const void *handles, size_t bytes);
 int mg_slab_info(mg_ctx *ctx, int *rank, int *nranks, int *own_planes, int *ghost, uint64_t *exchanges,
                  uint64_t *exchanged_bytes);
+/* bytes stored straight into other GPUs' memory by this handle's kernels (fused halo exchange + fused all-gather),
+ * and bytes moved by explicit exchanges (NCCL send/recv or peer copies), since creation */
+int mg_slab_traffic(mg_ctx *ctx, uint64_t *peer_store_bytes, uint64_t *exchange_bytes);
 /* MGPOISSON_CDEF_END */
 
 #ifdef __cplusplus

@@ -128,6 +128,7 @@ def lib():
         "mg_create_slab_local": (i, [i, i, i, i, i, i, C.POINTER(vp)]),
         "mg_create_slab_multi": (i, [i, i, i, i, i, pi, C.POINTER(vp)]),
         "mg_set_global_option": (i, [C.c_char_p, i]),
+        "mg_slab_traffic": (i, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "mg_slab_ipc_export": (i, [vp, vp, sz]),
         "mg_slab_ipc_attach": (i, [vp, vp, sz]),
         "mg_slab_info": (i, [vp, pi, pi, pi, pi, C.POINTER(u64), C.POINTER(u64)]),
@@ -299,6 +300,12 @@ class MultigridCUDA:
         self._ck(lib().mg_slab_info(self._h, *[C.byref(x) for x in v], C.byref(ex), C.byref(eb)))
         return dict(rank=v[0].value, nranks=v[1].value, own_planes=v[2].value, ghost=v[3].value,
                     exchanges=ex.value, exchanged_bytes=eb.value)
+
+    def slab_traffic(self):
+        """NVLink bytes so far: stored by this handle's kernels into other GPUs' memory, and moved by explicit exchanges."""
+        a, b = C.c_uint64(), C.c_uint64()
+        self._ck(lib().mg_slab_traffic(self._h, C.byref(a), C.byref(b)))
+        return dict(peer_store_bytes=a.value, exchange_bytes=b.value)
 
     def info(self):
         v = [C.c_int() for _ in range(5)]

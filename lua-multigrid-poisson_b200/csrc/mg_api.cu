@@ -691,4 +691,17 @@ int mg_slab_info(mg_ctx *ctx, int *rank, int *nranks, int *own_planes, int *ghos
     return MG_OK;
 }
 
+// NVLink traffic so far: bytes this handle's kernels stored straight into other GPUs' memory (fused halo exchange and
+// fused all-gather; counted per launch from the planes a pass sends), and bytes moved by explicit exchanges
+// (ncclSend/ncclRecv or peer copies: the ghost refresh after initCells / an upload, or every pass with slab_p2p = 0).
+int mg_slab_traffic(mg_ctx *ctx, uint64_t *peer_store_bytes, uint64_t *exchange_bytes)
+{
+    if (!ctx) return MG_EINVAL;
+    uint64_t b = 0;
+    for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) b += m->nvl_bytes;
+    if (peer_store_bytes) *peer_store_bytes = b;
+    if (exchange_bytes) *exchange_bytes = ctx->group ? ctx->group->exchanged_bytes : 0;
+    return MG_OK;
+}
+
 }  // extern "C"

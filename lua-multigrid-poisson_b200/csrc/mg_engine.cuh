@@ -117,6 +117,9 @@ struct mg_ctx {
     cudaGraphExec_t gexec = nullptr, rep_gexec = nullptr;
     size_t graph_nodes = 0, rep_nodes = 0;
     uint64_t launches = 0;
+    // bytes this rank's kernels stored into other GPUs' memory over NVLink (fused halo exchange and all-gather);
+    // a graph replay adds what its capture counted
+    uint64_t nvl_bytes = 0, cap_nvl_bytes = 0, graph_nvl_bytes = 0;
 
     bool prof_on = false;
     std::vector<mg::ProfRec> prof;
@@ -469,6 +472,13 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
                 a.rall_n = c->nranks;
                 for (int r = 0; r < c->nranks; ++r)
                     a.rall[r] = (r != c->rank && c->peer[r]) ? (R *)(c->peer[r] + roff) : nullptr;
+            }
+            {   // NVLink accounting: G boundary planes per neighbour (fine and, with RES, coarse), or the all-gather
+                const uint64_t nnb = (c->peer_lo ? 1 : 0) + (c->peer_hi ? 1 : 0);
+                uint64_t b = nnb * (uint64_t)std::min(c->G, nown) * c->plane_elems(lv) * c->elem;
+                if (Rout && c->dist[lv - 1]) b += nnb * (uint64_t)std::min(c->G, nown / 2) * c->plane_elems(lv - 1) * c->elem;
+                if (Rout && !c->dist[lv - 1]) b += (uint64_t)(c->nranks - 1) * (uint64_t)(nown / 2) * c->plane_elems(lv - 1) * c->elem;
+                (c->capturing ? c->cap_nvl_bytes : c->nvl_bytes) += b;
             }
             if (c->group && c->group->concurrent()) {  // the slabs run at the same time: handshake inside the kernel
                 a.hs = (unsigned long long *)c->arena;
@@ -1394,9 +1404,9 @@ inline int mg_ctx::vcycle()
         cudaStream_t saved = stream;
         MG_CK(this, cudaStreamSynchronize(saved));
         MG_CK(this, cudaStreamBeginCapture(cap_stream, cudaStreamCaptureModeThreadLocal));
-        stream = cap_stream; capturing = true;
+        stream = cap_stream; capturing = true; cap_nvl_bytes = 0;
         int rc = group ? eng->slab_vcycle(group) : eng->twogrid_fused(this, h, psi, f, top);
-        stream = saved; capturing = false;
+        stream = saved; capturing = false; graph_nvl_bytes = cap_nvl_bytes;
         cudaError_t e = cudaStreamEndCapture(cap_stream, &graph);
         if (rc) { if (graph) cudaGraphDestroy(graph); graph = nullptr; return rc; }
         if (e != cudaSuccess) { graph = nullptr; return fail_cuda(e, "cudaStreamEndCapture"); }
@@ -1407,6 +1417,7 @@ inline int mg_ctx::vcycle()
     }
     MG_CK(this, cudaGraphLaunch(gexec, stream));
     launches += graph_nodes;
+    nvl_bytes += graph_nvl_bytes;
     return MG_OK;
 }
 

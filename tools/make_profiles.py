@@ -1,14 +1,15 @@
 """Turns the ncu artefacts a gpurun call brought back into the committed summaries under profiles/.
 
-    python tools/make_profiles.py <launches.csv> <full.ncu-rep> [round_tag]
+    python tools/make_profiles.py launches <launches.csv> <tag> [config]     # per-kernel shares of one V-cycle
+    python tools/make_profiles.py full <full.ncu-rep> <tag> <config>         # --set full capture of the fused passes
+    python tools/make_profiles.py sass <tag>                                 # SASS mnemonic counts of the built library
 
-  * <launches.csv>: `ncu --metrics gpu__time_duration.sum --clock-control none -c N --csv --log-file ...
-                     python bench.py --steps 3 --warmup 3 --no-cpu`
-  * <full.ncu-rep>: `ncu --set full --clock-control none --import-source on -k regex:k_stream3d -s 0 -c 12 ...`
-                    (the 12 streaming-smoother launches of the first V-cycle at 512^3: L = 512, 256, 128 pre
-                    passes, then the post passes at 128, 256, 512)
-Writes profiles/<tag>_ncu_launches_3d512_f32.csv, profiles/<tag>_ncu_full_stream3d.md and
-profiles/dram_traffic.json (DRAM bytes per launch, read by bench.py for `roofline.traffic`).
+  config: 3d_512_float (default) | 2d_4096_float | 2d_2048_double -- the bench.py configuration the capture ran
+  * <launches.csv>: `ncu --metrics gpu__time_duration.sum --clock-control none -c N --csv --log-file ... python bench.py ...`
+  * <full.ncu-rep>: `ncu --set full --clock-control none --import-source on -k regex:'k_stream3d|k_warp2d|k_small' -c N ...`
+    of the FIRST V-cycle(s) bench.py runs (warm-up); launches are matched, in order, with the pass schedule of a cycle.
+`full` writes profiles/<tag>_ncu_full_<config>.md and merges DRAM bytes per launch into profiles/dram_traffic.json,
+which bench.py reads for `roofline.traffic` / `roofline.frac`.
 """
 import collections
 import csv
@@ -24,68 +25,118 @@ try:
     PEAK = float(json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"])
 except Exception:
     pass
-SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1}
+SCALE = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1, "us": 1e-6, "ms": 1e-3, "ns": 1e-9, "s": 1,
+         "usecond": 1e-6, "msecond": 1e-3, "nsecond": 1e-9, "second": 1}
 
 
 def short(name):
+    name = name.replace("(int)", "").replace("(bool)", "")
     m = re.match(r"void (?:mg::)?(\w+)<(.*?)>\(", name)
     return (m.group(1) + "<" + m.group(2) + ">") if m else name[:60]
 
 
-def launches(path, tag):
-    rows = [r for r in csv.reader(open(path)) if len(r) > 5 and r[0] != "ID"]
-    recs = [(short(r[4]), r[8], r[7], int(r[14])) for r in rows]
-    starts = [i for i, (n, g, b, t) in enumerate(recs) if n.startswith("k_stream3d<float, float, 4, 0, 0") and t > 400000]
-    a, b = starts[1], starts[2]
-    cyc = recs[a:b]
+def launches(path, tag, config):
+    rows = [r for r in csv.reader(l for l in open(path) if l.startswith('"'))]
+    hdr = rows[0]
+    iname, ival, igrid, iblock = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
+    recs = [(short(r[iname]), r[igrid], r[iblock], float(r[ival].replace(",", ""))) for r in rows[1:]]
+    # one V-cycle = from one launch of the first pass kernel of the cycle to the next
+    first = recs[[i for i, r in enumerate(recs) if r[0].startswith(("k_stream3d", "k_warp2d", "k_small"))][0]]
+    starts = [i for i, r in enumerate(recs) if r[:3] == first[:3]]
+    # the same kernel may appear twice per cycle: take the period as the distance between equal whole sequences
+    period = None
+    for cand in range(1, len(starts)):
+        p = starts[cand] - starts[0]
+        if starts[0] + 2 * p <= len(recs) and [r[0] for r in recs[starts[0]:starts[0] + p]] == [r[0] for r in recs[starts[0] + p:starts[0] + 2 * p]]:
+            period = p
+            break
+    if period is None:
+        period = len(recs) - starts[0]
+    a = starts[0] + period       # second cycle (warm)
+    cyc = recs[a:a + period] if a + period <= len(recs) else recs[starts[0]:starts[0] + period]
     tot = sum(t for *_, t in cyc)
     agg = collections.OrderedDict()
     for n, g, bk, t in cyc:
-        e = agg.setdefault((n, g, bk), [0, 0])
+        e = agg.setdefault((n, g, bk), [0, 0.0])
         e[0] += 1
         e[1] += t
-    out = ["# ncu launch list of one V-cycle (3-D 512^3 fp32, default tuning)",
-           "# command: ncu --metrics gpu__time_duration.sum --clock-control none -c 300 --csv --log-file launches.csv "
-           "python bench.py --steps 3 --warmup 3 --no-cpu   (right after the same command exited 0 without ncu)",
+    out = [f"# ncu launch list of one V-cycle ({config}, default tuning)",
+           "# command: ncu --metrics gpu__time_duration.sum --clock-control none -c N --csv --log-file launches.csv "
+           "python bench.py ... --steps 3 --warmup 3 --no-cpu   (right after the same command exited 0 without ncu)",
            "# times under ncu are cold-cache and serialised: compare SHARES with bench.py's vcycle.breakdown_ms, not absolutes",
            "kernel,grid,block,launches,total_us,share_pct"]
     for (n, g, bk), (c, t) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         out.append(f'"{n}","{g}","{bk}",{c},{t / 1e3:.1f},{100 * t / tot:.2f}')
     out.append(f"TOTAL,,,{len(cyc)},{tot / 1e3:.1f},100")
-    open(os.path.join(ROOT, "profiles", f"{tag}_ncu_launches_3d512_f32.csv"), "w").write("\n".join(out) + "\n")
-    return len(cyc), tot
+    open(os.path.join(ROOT, "profiles", f"{tag}_ncu_launches_{config}.csv"), "w").write("\n".join(out) + "\n")
+    print("\n".join(out[3:]))
 
 
-def full(rep, tag):
+def schedule(config):
+    """(kind, L, sweeps) of the fused-pass launches of one V-cycle, in launch order (mirrors EngineT::sweeps)."""
+    dim, size, real = config.split("_")
+    dim, size = int(dim[0]), int(size)
+    if dim == 3:
+        tb, minL, small = 4, 128, 16
+        pre = lambda: [("sweep", 4), ("sweep+residual_restrict", 3)]
+        post = lambda: [("sweep+prolong_add", 4), ("sweep", 3)]
+    else:
+        tb2 = 7 if real == "float" else 4
+        minL, small = 128, 64
+        if tb2 == 7:
+            pre = lambda: [("sweep+residual_restrict", 7)]
+            post = lambda: [("sweep+prolong_add", 7)]
+        else:
+            pre = lambda: [("sweep", 4), ("sweep+residual_restrict", 3)]
+            post = lambda: [("sweep+prolong_add", 4), ("sweep", 3)]
+    levels = []
+    L = size
+    while L >= minL:
+        levels.append(L)
+        L //= 2
+    order = [(k, L, s) for L in levels for k, s in pre()]
+    if dim == 2:
+        order.append(("small_levels", small, 14))
+    order += [(k, L, s) for L in reversed(levels) for k, s in post()]
+    return dim, size, real, order
+
+
+def full(rep, tag, config):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     hdr, units = rows[0], rows[1]
 
     def val(r, w):
         i = hdr.index(w)
-        return float(r[i]) * SCALE.get(units[i], 1)
+        return float(r[i].replace(",", "")) * SCALE.get(units[i], 1)
 
-    # launch order of the streaming smoother within a V-cycle at 512^3 (tb = 4)
-    order = [("sweep", 512, 4), ("sweep+residual_restrict", 512, 3), ("sweep", 256, 4), ("sweep+residual_restrict", 256, 3),
-             ("sweep", 128, 4), ("sweep+residual_restrict", 128, 3), ("sweep+prolong_add", 128, 4), ("sweep", 128, 3),
-             ("sweep+prolong_add", 256, 4), ("sweep", 256, 3), ("sweep+prolong_add", 512, 4), ("sweep", 512, 3)]
-    lines = [f"| launch | grid x block | time (ncu, cold) | DRAM read + write | DRAM / A_op | DRAM GB/s (% of {PEAK:.1f}) | issue slots busy | "
-             "regs | smem wavefronts (conflict replays) | LSU-smem busy |", "|---|---|---|---|---|---|---|---|---|---|"]
+    dim, size, real, order = schedule(config)
+    elem = 8 if real == "double" else 4
+    data = []
+    for r in rows[2:]:
+        kn = short(r[hdr.index("Kernel Name")])
+        if kn.startswith("k_stream3d"):
+            a = [x.strip() for x in kn[kn.index("<") + 1:-1].split(",")]
+            if len(a) >= 8 and a[7] == "2":
+                continue   # the (empty) guarded re-run kernel behind every branch-free pass
+        if kn.startswith(("k_stream3d", "k_warp2d", "k_small")):
+            data.append((kn, r))
+    lines = [f"| launch | kernel | grid x block | time (ncu, cold) | DRAM read + write | compulsory | DRAM / compulsory | DRAM GB/s (% of {PEAK:.1f}) | "
+             "issue slots busy | regs | smem wavefronts (conflict replays) | LSU-smem busy |", "|---|---|---|---|---|---|---|---|---|---|---|---|"]
     traffic = {}
-    for (kind, L, sw), r in zip(order, rows[2:]):
+    c = 2.0 ** -dim
+    for (kind, L, sw), (kn, r) in zip(order, data):
         name = f"{kind}[L={L},sweeps={sw}]"
-        want_pro, want_res = "prolong" in kind, "restrict" in kind
-        kn = r[hdr.index("Kernel Name")]
-        m = re.search(r"k_stream3d<float, float, (\d), (\d), (\d)", kn.replace("(int)", "").replace("(bool)", ""))
-        if m and (int(m.group(1)) != sw or bool(int(m.group(2))) != want_pro or bool(int(m.group(3))) != want_res):
-            name += " (?)"
         rd, wr, t = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum"), val(r, "gpu__time_duration.sum")
         wf = val(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")
         bc = val(r, "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum")
         cyc = val(r, "sm__cycles_elapsed.max")
-        aop = (3 * sw + (4.125 if (want_pro or want_res) else 0)) * 4 * L ** 3
-        lines.append(f"| `{name}` | {r[hdr.index('launch__grid_size')]} x {r[hdr.index('launch__block_size')]} | {t * 1e3:.3f} ms | "
-                     f"{rd / 1e9:.3f} + {wr / 1e9:.3f} GB | {(rd + wr) / 1e9:.3f} / {aop / 1e9:.3f} = {(rd + wr) / aop:.2f} | "
+        if kind == "small_levels":
+            comp = sum((6 + 2 * c) * float(l) ** dim for l in [L >> k for k in range(20)] if l > 1) * elem
+        else:
+            comp = (3 + (c if "+" in kind else 0)) * elem * float(L) ** dim
+        lines.append(f"| `{name}` | `{kn[:kn.index('<') + 40]}...` | {r[hdr.index('launch__grid_size')]} x {r[hdr.index('launch__block_size')]} | {t * 1e3:.4f} ms | "
+                     f"{rd / 1e9:.3f} + {wr / 1e9:.3f} GB | {comp / 1e9:.3f} GB | {(rd + wr) / comp:.2f} | "
                      f"{(rd + wr) / t / 1e9:.0f} ({(rd + wr) / t / 1e9 / PEAK * 100:.0f} %) | "
                      f"{float(r[hdr.index('smsp__issue_active.avg.pct_of_peak_sustained_active')]):.1f} % | "
                      f"{r[hdr.index('launch__registers_per_thread')]} | {wf / 1e6:.1f} M ({100 * bc / max(wf, 1):.1f} %) | "
@@ -96,32 +147,67 @@ def full(rep, tag):
     open(tmp, "w").write(src)
     summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_src_summary.py"), tmp, "12"],
                           capture_output=True, text=True).stdout
-    return lines, traffic, summ
+    head = [f"# ncu --set full capture of the fused passes of one V-cycle: {config} ({tag})", "",
+            "Command (on a B200, right after the same command exited 0 without ncu):", "", "```",
+            "ncu --set full --clock-control none --import-source on -k regex:'k_stream3d|k_warp2d|k_small' -c N -o prof \\",
+            "    python bench.py [--config ...] --steps 3 --warmup 3 --no-cpu", "```", "",
+            "DRAM = dram__bytes_read.sum + dram__bytes_write.sum of the launch; compulsory = what the fused launch cannot avoid",
+            "(read u and f, write u, + the coarse field it reads or writes). The (empty) guarded re-run kernels that follow the",
+            "branch-free fp32 passes are left out. Times under ncu are cold-cache and serialised.", ""]
+    tail = ["", "## Source-level summary of the first launch (`ncu --page source`, tools/ncu_src_summary.py)", "", "```"] + \
+        summ.splitlines() + ["```", ""]
+    note_path = os.path.join(ROOT, "profiles", f"{tag}_ncu_reading_{config}.md")
+    note = open(note_path).read().splitlines() if os.path.exists(note_path) else []
+    open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_{config}.md"), "w").write("\n".join(head + lines + [""] + note + tail))
+    tpath = os.path.join(ROOT, "profiles", "dram_traffic.json")
+    try:
+        tab = json.load(open(tpath))
+    except Exception:
+        tab = {}
+    tab[config] = traffic
+    src_note = tab.get("_source", {})
+    if not isinstance(src_note, dict):
+        src_note = {}
+    src_note[config] = f"profiles/{tag}_ncu_full_{config}.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch)"
+    tab["_source"] = src_note
+    json.dump(tab, open(tpath, "w"), indent=1)
+    print("\n".join(lines))
+
+
+def sass(tag):
+    lib = os.path.join(ROOT, "lua-multigrid-poisson_b200", "libmgpoisson.so")
+    txt = subprocess.run(["cuobjdump", "-sass", lib], capture_output=True, text=True).stdout
+    ops = collections.Counter()
+    for line in txt.splitlines():
+        m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
+        if m:
+            ops[m.group(1).split(".")[0]] += 1
+    want = ["UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "FADD2", "FFMA2", "FMUL2", "LDS", "STS", "SHFL", "LDTM", "STTM", "LDG", "STG",
+            "DADD", "DFMA", "DMUL", "HMMA", "BAR", "ST", "LD", "ATOMG", "RED", "VIMNMX3", "MUFU"]
+    log = os.path.join(ROOT, "lua-multigrid-poisson_b200", "csrc", "build.log")
+    spills = regs = ""
+    if os.path.exists(log):
+        t = open(log).read()
+        ents = re.findall(r"Compiling entry function '(\S+)'.*?\n.*?\n\s+(\d+) bytes stack frame, (\d+) bytes spill stores, (\d+) bytes spill loads\n.*?Used (\d+) registers", t)
+        hot = [e for e in ents if "k_stream3dIffLi4" in e[0] or "k_stream3dIffLi3" in e[0] or "k_warp2dIffLi7" in e[0] or "k_warp2dIddLi4" in e[0]]
+        spills = "\n".join(f"{subprocess.run(['c++filt', n], capture_output=True, text=True).stdout.strip()[:96]:96s} regs {r:>3s} spill stores {ss:>4s} B loads {sl:>4s} B"
+                           for n, st, ss, sl, r in hot)
+        regs = f"{len(ents)} kernels compiled; {sum(1 for e in ents if int(e[2]) > 0)} with spills (the double-arithmetic 2-D pipelines and S <= 2 variants at 80 registers)"
+    out = [f"# SASS summary of libmgpoisson.so ({tag}): cuobjdump -sass | mnemonic counts (static instructions, whole library)", ""]
+    out += [f"{k:10s} {ops.get(k, 0)}" for k in want]
+    out += ["", "# hot fp32 kernels (ptxas -v): mode 1 = branch-free, 2 = guarded re-run, 0 = guarded", spills, "", regs, ""]
+    open(os.path.join(ROOT, "profiles", f"{tag}_sass_summary.txt"), "w").write("\n".join(out))
+    print("\n".join(out[:30]))
 
 
 def main():
-    lcsv, rep = sys.argv[1], sys.argv[2]
-    tag = sys.argv[3] if len(sys.argv) > 3 else "r1"
-    n, tot = launches(lcsv, tag)
-    lines, traffic, summ = full(rep, tag)
-    head = [f"# ncu --set full capture of the streaming smoother `k_stream3d` ({tag}, final kernels)", "",
-            "Commands (on a B200, each right after the same command exited 0 without ncu):", "", "```",
-            "ncu --set full --clock-control none --import-source on -k regex:k_stream3d -s 0 -c 12 -o prof \\",
-            "    python bench.py --steps 3 --warmup 3 --no-cpu", "```", "",
-            "3-D 512^3 fp32, default tuning: tb = 4 (pre = [4][3+RES], post = [PRO+4][3]), tile 56 x 40 (+halo 64 x 48),",
-            "balanced persistent partition (one CTA per SM), f ring via TMA, packed fp32 arithmetic. The twelve launches are the",
-            "streaming-smoother passes of one V-cycle (L = 512, 256, 128). A_op = algorithmic bytes of the reference operators a",
-            "launch replaces (SURVEY 8(d)); DRAM = dram__bytes_read.sum + dram__bytes_write.sum of that launch.",
-            f"One V-cycle = {n} kernel launches, {tot / 1e6:.3f} ms under ncu (see the launch list next to this file).", ""]
-    tail = ["", "## Source-level summary of the first launch (`ncu --page source`, tools/ncu_src_summary.py)", "", "```"] + \
-        summ.splitlines() + ["```", ""]
-    note_path = os.path.join(ROOT, "profiles", f"{tag}_ncu_reading.md")
-    note = open(note_path).read().splitlines() if os.path.exists(note_path) else []
-    open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_stream3d.md"), "w").write("\n".join(head + lines + [""] + note + tail))
-    json.dump({"3d_512_float": {k: v for k, v in traffic.items() if "(?)" not in k},
-               "_source": f"profiles/{tag}_ncu_full_stream3d.md (ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum per launch)"},
-              open(os.path.join(ROOT, "profiles", "dram_traffic.json"), "w"), indent=1)
-    print("\n".join(lines))
+    cmd = sys.argv[1]
+    if cmd == "launches":
+        launches(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "3d_512_float")
+    elif cmd == "full":
+        full(sys.argv[2], sys.argv[3], sys.argv[4] if len(sys.argv) > 4 else "3d_512_float")
+    elif cmd == "sass":
+        sass(sys.argv[2])
 
 
 if __name__ == "__main__":
