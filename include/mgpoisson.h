@@ -86,6 +86,11 @@ int mg_set_tuning(mg_ctx *ctx, int tb, int small_L, int use_graph);
  * given to the streaming smoother), "tz" (planes per CTA of the streaming smoother; 0 = auto), "tb2" (2-D: sweeps per pass of the
  * warp-streaming smoother, 0..7), "warp2d_min_L", "ty" (2-D: rows per warp work item), "slab_p2p" (see below), "tma_promo" */
 int mg_set_option(mg_ctx *ctx, const char *name, int value);
+/* Relaxation weight of the Jacobi smoother, u + omega (J(u) - u). The reference is omega = 1 (cpu-raw.lua:34-44,
+ * 176-184: dest = (f - askew) / adiag, no weight) and that is the default, bit-identical to the reference path. Any other
+ * value is an EXTENSION (0 < omega < 2; e.g. 6/7 in 3-D, 4/5 in 2-D damp the mode the reference leaves undamped),
+ * offered so that a converging, labelled run can be timed next to the reference's; single GPU only. */
+int mg_set_omega(mg_ctx *ctx, double omega);
 int mg_get_info(mg_ctx *ctx, int *dim, int *size, int *real_kind, int *smooth, int *nlevels,
                 uint64_t *arena_bytes);
 

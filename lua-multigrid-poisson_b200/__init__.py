@@ -128,6 +128,7 @@ def lib():
         "mg_create_slab_local": (i, [i, i, i, i, i, i, C.POINTER(vp)]),
         "mg_create_slab_multi": (i, [i, i, i, i, i, pi, C.POINTER(vp)]),
         "mg_set_global_option": (i, [C.c_char_p, i]),
+        "mg_set_omega": (i, [vp, d]),
         "mg_slab_traffic": (i, [vp, C.POINTER(u64), C.POINTER(u64)]),
         "mg_slab_ipc_export": (i, [vp, vp, sz]),
         "mg_slab_ipc_attach": (i, [vp, vp, sz]),
@@ -293,6 +294,10 @@ class MultigridCUDA:
 
     def set_option(self, name, value):
         self._ck(lib().mg_set_option(self._h, name.encode(), int(value)))
+
+    def set_omega(self, omega: float):
+        """Weighted Jacobi (an extension: the reference is omega = 1, the default)."""
+        self._ck(lib().mg_set_omega(self._h, float(omega)))
 
     def slab_info(self):
         v = [C.c_int() for _ in range(4)]

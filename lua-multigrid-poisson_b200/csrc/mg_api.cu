@@ -157,6 +157,20 @@ int mg_set_option(mg_ctx *ctx, const char *name, int value)
     return MG_OK;
 }
 
+// Weighted Jacobi u + omega * (J(u) - u). NOT in the reference, whose smoother is omega = 1 (cpu-raw.lua:34-44,176-184)
+// and does not converge for it; omega = 1 (the default) keeps every result bit-identical to the
+// reference path. omega != 1 is a labelled extension for time-to-solution reports: the level visits then run the
+// one-sweep-per-launch kernels (the temporally blocked kernels implement the reference smoother only).
+int mg_set_omega(mg_ctx *ctx, double omega)
+{
+    CTX_OR_FAIL(ctx);
+    if (!(omega > 0.0 && omega < 2.0)) return ctx->fail(MG_EINVAL, "mg_set_omega: 0 < omega < 2");
+    if (ctx->group && omega != 1.0) return ctx->fail(MG_EUNSUPPORTED, "mg_set_omega: slabs run the reference smoother (omega = 1) only");
+    ctx->omega = omega;
+    ctx->drop_graph();
+    return MG_OK;
+}
+
 int mg_get_info(mg_ctx *ctx, int *dim, int *size, int *real_kind, int *smooth, int *nlevels,
                 uint64_t *arena_bytes)
 {

@@ -85,6 +85,7 @@ struct mg_ctx {
     int lockstep_opt = 1;    // lock-step partition of the streaming smoother: whole columns below zsplit + helper CTAs above
     int tma_promo = 0;       // L2 promotion of the TMA descriptors: 0 none (least DRAM over-fetch), 1 64 B, 2 128 B, 3 256 B
     int stream_flags = 0;    // debug switches of the streaming smoother (see Stream3DArgs::flags)
+    double omega = 1.0;      // relaxation weight of the Jacobi smoother: 1 = the reference (mg_set_omega)
     int fastdiv_opt = 1;     // fp32 streaming smoother: branch-free division kernel + guarded re-run kernel (0: guarded kernel only)
     int fast_min_L = 256;    // ... at levels at least this wide (128^3: the second launch costs what the branches cost)
     int tz_override = 0;     // planes per CTA of the streaming smoother (0 = cost model)
@@ -260,7 +261,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
     {
         dim3 b = block_for(L), g = grid_for(DIM, L, b);
         k_jacobi<R, A, DIM><<<g, b, 0, c->stream>>>((R *)dest, (const R *)u, (const R *)f, L,
-                                                    make_coef<A>(DIM, h));
+                                                    make_coef<A>(DIM, h, c->omega));
         MG_LAUNCH_CHECK(c);
         return MG_OK;
     }
@@ -807,13 +808,14 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
     int sweeps(mg_ctx *c, int lv, R *&cur, R *&oth, const R *f, double h, int n, const R *Vp, R *Rout)
     {
         const int L = 1 << lv;
-        const Coef<A> cf = make_coef<A>(DIM, h);
+        const Coef<A> cf = make_coef<A>(DIM, h, c->omega);
+        const bool ref_omega = c->omega == 1.0;   // the fused multi-sweep kernels implement the reference's omega = 1 only
         if constexpr (DIM == 2) {
-            if (c->tb2 >= 1 && L >= c->warp2d_min_L && n >= 1 && !(Vp && Rout && n <= c->tb2))
+            if (ref_omega && c->tb2 >= 1 && L >= c->warp2d_min_L && n >= 1 && !(Vp && Rout && n <= c->tb2))
                 return sweeps_warp2d(c, L, cur, oth, f, cf, n, Vp, Rout);
         }
         if constexpr (DIM == 3) {
-            if (c->tb >= 1 && L >= c->stream_min_L && n >= 1 && !(Vp && Rout && n <= c->tb))
+            if (ref_omega && c->tb >= 1 && L >= c->stream_min_L && n >= 1 && !(Vp && Rout && n <= c->tb))
                 return sweeps_stream3d(c, lv, cur, oth, f, cf, n, Vp, Rout);
         }
         dim3 b = block_for(L), g = grid_for(DIM, L, b);
@@ -892,7 +894,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             a.u[l] = l == lv ? u : (R *)c->V[l];
             a.f[l] = l == lv ? f : (const R *)c->R[l];
             a.w[l] = (R *)c->W[l];
-            a.coef[l] = make_coef<A>(DIM, hl);
+            a.coef[l] = make_coef<A>(DIM, hl, c->omega);
         }
         size_t n = c->level_elems(lv);
         int threads = n >= 1024 ? 1024 : (n >= 256 ? 256 : 64);
@@ -1049,11 +1051,55 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
 
     int residual_norm(mg_ctx *c, double *rms) override
     {
-        if (c->group) return c->fail(MG_EUNSUPPORTED, "mg_residual_norm: not available on slabs yet");
         // uses the partner of psi as scratch for r; W[top] is free outside a V-cycle
         const int top = c->nlevels - 1;
+        int rc;
+        if (c->group) {
+            // slabs: every rank computes r on the planes it owns (psi's ghost planes are kept fresh by the smoother
+            // passes; after initCells / an upload they are refreshed first), sums its squares, and the sums are added
+            if constexpr (DIM == 3) {
+                SlabGroup *g = c->group;
+                mg_ctx *c0 = g->m[0];
+                if (c0->u_ghost_dirty || !c0->p2p) {
+                    if ((rc = slab_exchange(g, c0->arena_off(c0->psi), top, c0->G, true))) return rc;
+                    if (c0->p2p) for (mg_ctx *m : g->m) m->u_ghost_dirty = false;
+                }
+                const Coef<A> cf = make_coef<A>(DIM, 1.0 / c->size);
+                double tot = 0;
+                for (mg_ctx *m : g->m) {
+                    if ((rc = m->activate())) return rc;
+                    dim3 b = block_for(m->size), gr = grid_for(DIM, m->size, b);
+                    gr.z = (unsigned)m->nzl[top];
+                    if (g->concurrent() && m->p2p) {   // the neighbours' last pass fills our ghost planes: wait for it
+                        k_slab_wait_neighbours<<<1, 32, 0, m->stream>>>((unsigned long long *)m->arena, m->peer_lo != nullptr, m->peer_hi != nullptr);
+                        MG_LAUNCH_CHECK(m);
+                    }
+                    k_residual_slab<R, A><<<gr, b, 0, m->stream>>>((R *)m->W[top], (const R *)m->f, (const R *)m->psi, m->size, m->G, cf);
+                    MG_LAUNCH_CHECK(m);
+                    k_sumsq_partial<R><<<m->npartial, 256, 0, m->stream>>>((const R *)m->W[top] + m->own_off_elems(top), m->own_elems(top), m->d_partial);
+                    MG_LAUNCH_CHECK(m);
+                    if (g->nccl) {
+                        k_final_sum<<<1, 1024, 0, m->stream>>>(m->d_partial, m->npartial, m->d_scalar);
+                        MG_LAUNCH_CHECK(m);
+                        int e = g->api->AllReduce(m->d_scalar, m->d_scalar, 1, NcclApi::kFloat64, NcclApi::kSum, g->comm, m->stream);
+                        if (e) return m->fail(MG_ECUDA, g->api->GetErrorString(e));
+                        MG_CK(m, cudaMemcpyAsync(m->h_scalar, m->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, m->stream));
+                        MG_CK(m, cudaStreamSynchronize(m->stream));
+                        tot = *m->h_scalar;
+                    } else {
+                        double part;
+                        if ((rc = reduce_to_host(m, &part))) return rc;
+                        tot += part;
+                    }
+                }
+                *rms = std::sqrt(tot / (double)c->N);
+                return MG_OK;
+            } else {
+                return c->fail(MG_EUNSUPPORTED, "slab decomposition is 3-D only");
+            }
+        }
         R *scratch = (R *)c->W[top];
-        int rc = residual(c, c->size, scratch, c->f, c->psi, 1.0 / c->size);
+        rc = residual(c, c->size, scratch, c->f, c->psi, 1.0 / c->size);
         if (rc) return rc;
         k_sumsq_partial<R><<<c->npartial, 256, 0, c->stream>>>(scratch, c->N, c->d_partial);
         MG_LAUNCH_CHECK(c);

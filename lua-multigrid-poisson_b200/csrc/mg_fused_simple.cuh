@@ -47,7 +47,9 @@ __global__ void k_sweep_pp(R *__restrict__ dst, const R *__restrict__ src, const
             S = Ar<A>::add(Ar<A>::add(S, zl), zr);
         }
     }
-    dst[idx] = (R)jacobi_point<DIM, A>(S, (A)f[idx], c);
+    A out = jacobi_point<DIM, A>(S, (A)f[idx], c);
+    if (c.weighted) out = relax<A>(out, PROLONG ? corrected<R, A, DIM>(src, V, i, j, k, L, idx) : (A)src[idx], c);
+    dst[idx] = (R)out;
 }
 
 // u += prolong(V) in place (only needed when a level visit has zero post-sweeps)

@@ -58,9 +58,11 @@ template <typename A> struct Coef {
     A cneg;    // 2-D: -h^2/4 (= 1/adiag, exact)
     A yneg;    // 3-D: RN(1/adiag)
     A nadiag;  // -adiag
+    A omega;   // relaxation weight; the reference is omega = 1 (cpu-raw.lua:34-44), anything else is a labelled extension
+    int weighted;   // omega != 1: the un-fused kernels apply u + omega * (Jacobi(u) - u); 0 keeps the reference arithmetic
 };
 
-template <typename A> static inline Coef<A> make_coef(int dim, double h)
+template <typename A> static inline Coef<A> make_coef(int dim, double h, double omega = 1.0)
 {
     Coef<A> c;
     double h2 = h * h;
@@ -72,7 +74,15 @@ template <typename A> static inline Coef<A> make_coef(int dim, double h)
     c.cneg = (A)1 / c.adiag;
     c.yneg = (A)1 / c.adiag;
     c.nadiag = -c.adiag;
+    c.omega = (A)omega;
+    c.weighted = omega != 1.0;
     return c;
+}
+
+// weighted Jacobi (NOT in the reference, which is omega = 1): u + omega * (J(u) - u), two roundings on top of J
+template <typename A> __device__ __forceinline__ A relax(A jac, A u, const Coef<A> &c)
+{
+    return c.weighted ? Ar<A>::fma(c.omega, Ar<A>::sub(jac, u), u) : jac;
 }
 
 // numerator of the Jacobi update: RN(f - S/h^2)

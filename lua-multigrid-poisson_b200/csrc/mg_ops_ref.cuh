@@ -37,7 +37,7 @@ __global__ void k_jacobi(R *__restrict__ dest, const R *__restrict__ u, const R 
     if (i >= L || j >= L) return;
     size_t idx = (size_t)i + (size_t)L * ((size_t)j + (size_t)L * k);
     A S = stencil_sum<DIM, R, A>(u, i, j, k, L, idx);
-    dest[idx] = (R)jacobi_point<DIM, A>(S, (A)f[idx], c);
+    dest[idx] = (R)relax<A>(jacobi_point<DIM, A>(S, (A)f[idx], c), (A)u[idx], c);
 }
 
 // cpu-raw.lua:46-57 calcResidual / gpu.lua:104-124
@@ -51,6 +51,24 @@ __global__ void k_residual(R *__restrict__ r, const R *__restrict__ f, const R *
     if (i >= L || j >= L) return;
     size_t idx = (size_t)i + (size_t)L * ((size_t)j + (size_t)L * k);
     A S = stencil_sum<DIM, R, A>(u, i, j, k, L, idx);
+    r[idx] = (R)residual_point<A>(S, (A)f[idx], (A)u[idx], c);
+}
+
+// calcResidual on the planes [plane0, plane0 + gridDim.z) of a z-slab (3-D): the z-neighbours are read from the
+// planes above and below unconditionally -- ghost planes hold the neighbouring rank's values, or +0 outside the grid,
+// which is the reference's "a neighbour outside the grid reads 0" (cpu-raw.lua:36-39)
+template <typename R, typename A>
+__global__ void k_residual_slab(R *__restrict__ r, const R *__restrict__ f, const R *__restrict__ u, int L, int plane0, Coef<A> c)
+{
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    int j = blockIdx.y * blockDim.y + threadIdx.y;
+    if (i >= L || j >= L) return;
+    const size_t sL = (size_t)L, sLL = sL * sL;
+    const size_t idx = (size_t)i + sL * j + sLL * (size_t)(plane0 + (int)blockIdx.z);
+    A xl = i > 0 ? (A)u[idx - 1] : (A)0, xr = i < L - 1 ? (A)u[idx + 1] : (A)0;
+    A yl = j > 0 ? (A)u[idx - sL] : (A)0, yr = j < L - 1 ? (A)u[idx + sL] : (A)0;
+    A S = Ar<A>::add(Ar<A>::add(Ar<A>::add(xl, xr), yl), yr);
+    S = Ar<A>::add(Ar<A>::add(S, (A)u[idx - sLL]), (A)u[idx + sLL]);
     r[idx] = (R)residual_point<A>(S, (A)f[idx], (A)u[idx], c);
 }
 

@@ -124,6 +124,15 @@ __global__ void k_slab_wait_all(SlabPeers p)
     if (r < p.nranks) s3_wait_counter(own + HS_AG_FROM + r, e, own);
 }
 
+// ahead of anything that READS this rank's ghost planes outside a smoother pass (the residual norm): both neighbours
+// must have completed as many passes as this rank (their last pass is what fills our ghosts)
+__global__ void k_slab_wait_neighbours(unsigned long long *hs, int has_lo, int has_hi)
+{
+    const unsigned long long n = s3_ld_acquire_sys(hs + HS_DONE);
+    if (threadIdx.x == 0 && has_lo) s3_wait_counter(hs + HS_FROM_LO, n, hs);
+    if (threadIdx.x == 1 && has_hi) s3_wait_counter(hs + HS_FROM_HI, n, hs);
+}
+
 struct SlabGroup {
     std::vector<mg_ctx *> m;  // LOCAL / MULTI: every rank's context; NCCL: this rank's only
     int nranks = 1;

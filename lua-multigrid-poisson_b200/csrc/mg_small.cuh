@@ -51,7 +51,9 @@ __device__ __forceinline__ void cta_sweep(R *dst, const R *src, const R *f, cons
                 S = Ar<A>::add(Ar<A>::add(S, zl), zr);
             }
         }
-        dst[idx] = (R)jacobi_point<DIM, A>(S, (A)f[idx], c);
+        A out = jacobi_point<DIM, A>(S, (A)f[idx], c);
+        if (c.weighted) out = relax<A>(out, PROLONG ? corrected<R, A, DIM>(src, V, i, j, k, L, (size_t)idx) : (A)src[idx], c);
+        dst[idx] = (R)out;
     }
 }
 
@@ -103,7 +105,7 @@ __global__ void __launch_bounds__(1024, 1) k_small_vcycle(SmallArgs<R, A> a)
     if (threadIdx.x == 0) {
         A S = Ar<A>::add(Ar<A>::add(Ar<A>::add((A)0, (A)0), (A)0), (A)0);
         if (DIM == 3) S = Ar<A>::add(Ar<A>::add(S, (A)0), (A)0);
-        a.u[0][0] = (R)jacobi_point<DIM, A>(S, (A)a.f[0][0], a.coef[0]);
+        a.u[0][0] = (R)relax<A>(jacobi_point<DIM, A>(S, (A)a.f[0][0], a.coef[0]), (A)a.u[0][0], a.coef[0]);
     }
     __syncthreads();
     // ---- ascend: prolong, add, post-smooth (cpu-raw.lua:221-236)

@@ -73,6 +73,11 @@ int mg_set_tuning(mg_ctx *ctx, int tb, int small_L, int use_graph);
  * given to the streaming smoother), "tz" (planes per CTA of the streaming smoother; 0 = auto), "tb2" (2-D: sweeps per pass of the
  * warp-streaming smoother, 0..7), "warp2d_min_L", "ty" (2-D: rows per warp work item), "slab_p2p" (see below), "tma_promo" */
 int mg_set_option(mg_ctx *ctx, const char *name, int value);
+/* Relaxation weight of the Jacobi smoother, u + omega (J(u) - u). The reference is omega = 1 (cpu-raw.lua:34-44,
+ * 176-184: dest = (f - askew) / adiag, no weight) and that is the default, bit-identical to the reference path. Any other
+ * value is an EXTENSION (0 < omega < 2; e.g. 6/7 in 3-D, 4/5 in 2-D damp the mode the reference leaves undamped),
+ * offered so that a converging, labelled run can be timed next to the reference's; single GPU only. */
+int mg_set_omega(mg_ctx *ctx, double omega);
 int mg_get_info(mg_ctx *ctx, int *dim, int *size, int *real_kind, int *smooth, int *nlevels,
                 uint64_t *arena_bytes);
 
@@ -266,18 +271,72 @@ function MultigridCUDA:setbuffer(which, L, cpuMem)
 	check(self, lib.mg_upload(self.handle, which, L, cpuMem, L^self.dim * ffi.sizeof(ctypes[self.real])))
 end
 
+-- cpu-raw.lua:126-140: with `debugging` on, print a field the way the CPU versions do, so that runs can be diffed:
+-- the name, then L rows of L values, each preceded by a blank (io.write(' ', im[j+L*i])); a non-finite value is an error.
+-- `im` is HOST memory here (indexable from 0): a getbuffer() result or a stage record of the device trace.
+-- dim = 3: L planes of that layout follow each other (the reference is 2-D only).
+function MultigridCUDA:show(name, im, L)
+	if not self.debugging then return end
+	print(name)
+	local rows = self.dim == 3 and L * L or L
+	for i=0,rows-1 do
+		for j=0,L-1 do
+			io.write(' ', im[j+L*i])
+		end
+		print()
+	end
+	for i=0,rows*L-1 do
+		if not math.isfinite(im[i]) then
+			error("found a nan")
+		end
+	end
+end
+
+-- The reference's twoGrid calls show() between its operators (cpu-raw.lua:187-236). Here the whole cycle runs on the
+-- device; with `debugging` the library runs one kernel per reference operator (MG_MODE_REFSEQ) and records every field
+-- the reference would have shown, in its order -- replayed through show() afterwards.
+function MultigridCUDA:showTrace()
+	local n = tonumber(lib.mg_trace_count(self.handle))
+	local name, L = ffi.new'char[1]', ffi.new'int[1]'
+	local data, bytes = ffi.new'const void*[1]', ffi.new'size_t[1]'
+	for i=0,n-1 do
+		check(self, lib.mg_trace_get(self.handle, i, name, L, data, bytes))
+		self:show(string.char(name[0]), ffi.cast(ctypes[self.real]..'*', data[0]), L[0])
+	end
+	check(self, lib.mg_trace_clear(self.handle))
+end
+
+-- conjugate gradient on the same operator, b = f, x = psi as found (converge-multigrid-vs-krylov.lua:38-69, whose
+-- solver.conjgrad is an un-vendored library): returns the number of iterations and the per-iteration histories
+-- err = |r|/|b| and |x|_inf (what the experiment's errorCallback records, :62-64)
+function MultigridCUDA:conjgrad(maxiter, epsilon)
+	maxiter = maxiter or 1000
+	local errs, linf = ffi.new('double[?]', maxiter), ffi.new('double[?]', maxiter)
+	local n = ffi.new'int[1]'
+	check(self, lib.mg_cg(self.handle, maxiter, epsilon or 1e-20, errs, linf, n))
+	return n[0], errs, linf
+end
+
+function MultigridCUDA:initCells()								-- cpu-raw.lua:8-20
+	check(self, lib.mg_init_cells(self.handle))
+end
+
 function MultigridCUDA:inPlaceIterativeSolver(L, u, f, h)		-- cpu-raw.lua:176-184
 	check(self, lib.mg_smooth(self.handle, L, u, f, h, 1))
 end
 
 function MultigridCUDA:twoGrid(h, u, f, L)						-- cpu-raw.lua:186-237
+	if self.debugging then check(self, lib.mg_trace_enable(self.handle, 1)) end
 	check(self, lib.mg_twogrid(self.handle, h, u, f, L))
+	if self.debugging then self:showTrace() end
 end
 
 function MultigridCUDA:step()									-- cpu.lua:196-206
 	if self.zeroCorrections then check(self, lib.mg_zero_corrections(self.handle)) end		-- cpu.lua:138
 	local err = ffi.new'double[1]'
+	if self.debugging then check(self, lib.mg_trace_enable(self.handle, 1)) end
 	check(self, lib.mg_step(self.handle, err))
+	if self.debugging then self:showTrace() end		-- the dumps of this cycle's twoGrid, in the reference's order
 	return err[0]
 end
 

@@ -240,6 +240,18 @@ def _str_match(s, pat, init=1):
     return tuple(m.groups()) if m.groups() else (m.group(0),)
 
 
+def _str_gmatch(s, pat):
+    """string.gmatch for patterns without anchors: an iterator over the matches (captures, or the whole match)"""
+    rx = re.compile(lua_pattern_to_regex(pat))
+    it = rx.finditer(s)
+
+    def step(*_):
+        for m in it:
+            return tuple(m.groups()) if m.groups() else (m.group(0),)
+        return None
+    return (step, None, None)
+
+
 def _str_find(s, pat, init=1, plain=None):
     if lua_truth(plain):
         i = s.find(pat, int(init) - 1)
@@ -259,7 +271,8 @@ class _StringLib:
         self.fns = {"lower": lambda s, *_: s.lower(), "upper": lambda s, *_: s.upper(), "len": lambda s: float(len(s)),
                     "sub": lambda s, i=1, j=-1: s[(int(i) - 1 if i > 0 else max(len(s) + int(i), 0)):(int(j) if j >= 0 else len(s) + int(j) + 1)],
                     "rep": lambda s, n: s * int(n), "match": _str_match, "find": _str_find, "format": _str_format,
-                    "byte": lambda s, i=1: float(ord(s[int(i) - 1])), "char": lambda *a: "".join(chr(int(x)) for x in a)}
+                    "byte": lambda s, i=1: float(ord(s[int(i) - 1])), "char": lambda *a: "".join(chr(int(x)) for x in a),
+                    "gmatch": _str_gmatch}
 
     def get(self, k):
         return self.fns.get(k)
@@ -1154,13 +1167,32 @@ class Interpreter:
         g["math"] = self.table_from(self.math_functions())
         io = LuaTable()
         io.set("write", self._io_write)
+        io.set("open", self._io_open)
         g["io"] = io
+        # the few `table` functions the shipped driver scripts (lua/test/*.lua) use
+        def _t_insert(t, a, b=None):
+            if b is None:
+                t.set(t.length() + 1, a)
+            else:
+                n = t.length()
+                for k in range(n, int(a) - 1, -1):
+                    t.set(k + 1, t.get(k))
+                t.set(int(a), b)
+        def _t_concat(t, sep="", i=1, j=None):
+            j = t.length() if j is None else int(j)
+            return (sep.join(lua_tostring(t.get(k)) for k in range(int(i), j + 1)),)
+        g["table"] = self.table_from({"insert": _t_insert, "concat": _t_concat,
+                                      "unpack": lambda t, i=1, j=None: self._unpack(t, i, j)})
         g["string"] = STRING_LIB.as_table()
         import os as _os
         import time as _time
         def _exit(code=0):
             raise LuaExit(int(code or 0))
+        def _execute(cmd=None):
+            import subprocess as _sp
+            return (float(_sp.call(cmd, shell=True)),) if cmd is not None else (True,)
         g["os"] = self.table_from({"getenv": lambda k: (_os.environ.get(k),), "clock": lambda: _time.process_time(),
+                                   "execute": _execute,
                                    "time": lambda: float(int(_time.time())), "exit": _exit})
         # LuaJIT loads its `bit` library as a global as well (gpu.lua:257 uses it without a require)
         g["bit"] = self.table_from({"lshift": lambda a, n: float(int(a) << int(n)), "rshift": lambda a, n: float(int(a) >> int(n)),
@@ -1216,6 +1248,19 @@ class Interpreter:
         self.written.extend(args)
         if self._stdout is not None:
             self._stdout.write("".join(lua_tostring(a) for a in args))
+
+    def _io_open(self, name, mode="r"):
+        """io.open for the driver scripts: a file object with :write, :read('*a'), :lines-free, :flush, :close"""
+        try:
+            fh = open(name, mode.replace("b", ""))
+        except OSError as e:
+            return (None, str(e))
+        f = LuaTable()
+        f.set("write", lambda self_, *a: (fh.write("".join(lua_tostring(x) for x in a)), self_)[1])
+        f.set("read", lambda self_, fmt="*l": (fh.read() if str(fmt).lstrip("*").startswith("a") else (fh.readline().rstrip("\n") or None),))
+        f.set("flush", lambda self_: fh.flush())
+        f.set("close", lambda self_: fh.close())
+        return (f,)
 
     def _error(self, msg=None, level=None):
         raise LuaError(lua_tostring(msg))

@@ -73,7 +73,7 @@ class CArrayData:
         v = self.buf[i]
         if self.is_ptr:
             return CPointer(v)
-        return float(v) if not isinstance(v, bytes) else v
+        return float(v) if not isinstance(v, bytes) else float(v[0])     # char: a number, like LuaJIT
 
     def lua_setindex(self, k, v):
         i = int(k)
@@ -89,6 +89,22 @@ class CArrayData:
     def numpy(self, dtype):
         import numpy as np
         return np.frombuffer(self.buf, dtype=dtype, count=self.n).copy()
+
+
+class CTypedPointer(CPointer):
+    """`T*` obtained by ffi.cast: indexable (from 0) memory somebody else owns."""
+
+    def __init__(self, elem, addr):
+        super().__init__(addr)
+        self.elem = elem
+        self.ct = _SCALARS[elem]
+
+    def lua_index(self, k):
+        v = self.ct.from_address(self.addr + int(k) * C.sizeof(self.ct)).value
+        return float(v) if not isinstance(v, bytes) else float(v[0])
+
+    def lua_setindex(self, k, v):
+        self.ct.from_address(self.addr + int(k) * C.sizeof(self.ct)).value = float(v) if self.elem in ("double", "float") else int(v)
 
 
 class _Proto:
@@ -169,7 +185,7 @@ class FFI:
     # ---- the module table for `require 'ffi'`
     def module(self):
         return ml.Interpreter.table_from({"cdef": self.cdef, "load": self.load, "new": self.new, "gc": self.gc,
-                                          "string": self.string, "sizeof": self.sizeof})
+                                          "string": self.string, "sizeof": self.sizeof, "cast": self.cast})
 
     def cdef(self, text):
         text = re.sub(r"/\*.*?\*/", " ", text, flags=re.S)
@@ -248,6 +264,14 @@ class FFI:
         for i, v in enumerate(init):
             arr.lua_setindex(i, v)
         return arr
+
+    def cast(self, ct, v):
+        """ffi.cast('T*', pointer): a typed view of memory the library owns"""
+        m = re.match(r"^\s*(?:const\s+)?([\w ]+?)\s*\*\s*$", ct)
+        if not m or m.group(1) not in _SCALARS:
+            raise ml.LuaError(f"ffi.cast: unsupported ctype '{ct}'")
+        addr = v.addr if isinstance(v, (CPointer, CArrayData)) else int(v or 0)
+        return CTypedPointer(m.group(1), addr)
 
     def gc(self, cdata, fin):
         cdata._fin = fin

@@ -29,6 +29,7 @@ def main():
     for real, p2p, smooth in (("float", True, 7), ("double", True, 7), ("float", False, 7), ("float", True, 4), ("float", True, 8)):
         s = pkg.create_distributed(size, real, dim=3, p2p=p2p, smooth=smooth)
         errs = [s.step() for _ in range(3)]
+        rn = s.residual_norm()
         mine = torch.from_numpy(s.psi.download()).cuda()
         parts = [torch.empty_like(mine) for _ in range(world)]
         dist.all_gather(parts, mine)
@@ -40,6 +41,7 @@ def main():
             ref_errs = [one.step() for _ in range(3)]
             same = full.tobytes() == one.psi.download().tobytes()
             eok = all(abs(a - b) <= 1e-9 * abs(b) for a, b in zip(errs, ref_errs))
+            eok = eok and abs(rn - one.residual_norm()) <= 1e-9 * rn
             print(f"[mgpu_check] {world} GPUs, {size}^3 {real}, smooth={smooth}, {'fused peer-store' if p2p else 'NCCL send/recv'} halos: psi bit-identical to 1 GPU: {same}; "
                   f"err {errs} vs {ref_errs}: {eok}; slab info {s.slab_info()}", flush=True)
             ok = ok and same and eok

@@ -54,6 +54,8 @@ def test_one_process_many_gpus_matches_single_gpu(mgp, real, smooth):
         one.psi.upload(u); many.psi.upload(u)
         assert abs(one.step() - many.step()) <= 1e-9
         assert one.psi.download().tobytes() == many.psi.download().tobytes()
+        r1, r2 = one.residual_norm(), many.residual_norm()
+        assert abs(r1 - r2) <= 1e-9 * r1
         tr = many.slab_traffic()
         assert tr["peer_store_bytes"] > 0
     finally:

@@ -38,6 +38,29 @@ def test_local_slab_group_matches_single_solver(mgp, monkeypatch, size, P, real,
         assert_bits_equal(grp.Vs[L].download(), one.Vs[L].download(), f"Vs[{L}]")
         assert_bits_equal(grp.Rs[L].download(), one.Rs[L].download(), f"Rs[{L}]")
     assert (grp.slab_info()["exchanges"] > 6) == (p2p == 0)
+    # the true residual norm and the cpu.lua variant (corrections re-zeroed) are available on slabs as well
+    r1, rg = one.residual_norm(), grp.residual_norm()
+    assert abs(r1 - rg) <= err_rtol(size ** 3) * r1, (r1, rg)
+    one.zero_corrections(); grp.zero_corrections()
+    e1, eg = one.step(), grp.step()
+    assert abs(e1 - eg) <= err_rtol(size ** 3) * e1
+    assert_bits_equal(grp.psi.download(), one.psi.download(), "psi after a cycle with re-zeroed corrections")
+    one.close(); grp.close()
+
+
+@pytest.mark.parametrize("smooth", [1, 2, 4, 5, 8])
+def test_local_slab_group_other_sweep_counts(mgp, monkeypatch, smooth):
+    """smooth = 4 and 8 give an odd number of ping-pong passes per level visit with tb = 4 unless the slab schedule
+    pads them (one extra, shorter, post-smoothing pass); the result is the same field bit for bit."""
+    monkeypatch.setenv("MGPOISSON_SLAB_MIN_PLANES", "8")
+    one = mgp.MultigridCUDA(128, "float", dim=3, out=False, smooth=smooth)
+    grp = mgp.MultigridCUDA(128, "float", dim=3, out=False, local_slabs=4, smooth=smooth)
+    for cyc in range(2):
+        e1, eg = one.step(), grp.step()
+        assert abs(e1 - eg) <= err_rtol(128 ** 3) * e1, (cyc, e1, eg)
+    assert_bits_equal(grp.psi.download(), one.psi.download(), f"smooth={smooth}")
+    with pytest.raises(mgp.MGError):
+        grp.set_option("tb", 0)          # the slab schedule needs the streaming smoother
     one.close(); grp.close()
 
 

@@ -168,3 +168,110 @@ def test_lua_class_in_cpu_lua_style_matches_cpu_lua(size):
     psi = ml.lua_call(ml.lua_index(obj, "getbuffer"), [obj, lib.lua_index("MG_BUF_PSI"), float(size)])[0]
     _bits_equal(psi.numpy(np.float64), g[f"psi{steps}"], f"psi after {steps} cycles of solve()")
     ffi.close()
+
+
+def _show_text(name, a, L):
+    """cpu-raw.lua:126-134: the name, then L rows of L values, each preceded by a blank"""
+    a = np.asarray(a).ravel()
+    rows = ["".join(" " + ml.lua_tostring(float(a[j + L * i])) for j in range(L)) for i in range(L)]
+    return name + "\n" + "".join(r + "\n" for r in rows)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fixture,real", [("ref_2d_16_f64", "double"), ("ref_2d_8_f32", "float_acc64")])
+def test_debugging_show_dumps_have_the_reference_text(fixture, real):
+    """`debugging = true`: run() prints, for every field the reference's twoGrid shows (cpu-raw.lua:187-236), the text
+    its show() prints (:126-134), in the reference's order. Expected text = that layout applied to the stage dumps of the
+    reference-source run (tests/golden/ref_2d_*.npz). (cpu-raw.lua's stray `print('L', L)` / `print('smooth', i)` lines
+    are not part of show() and are not reproduced.)"""
+    g = np.load(os.path.join(GOLDEN, fixture + ".npz"))
+    size = int(g["meta"][1])
+    names, Ls = [str(n) for n in g["trace_names"]], [int(l) for l in g["trace_L"]]
+    per_cycle = len(names) // 2
+    ffi = minilua_ffi.FFI(search_dirs=[PKG])
+    out = io.StringIO()
+    it = ml.Interpreter(modules={"ffi": ffi.module(), "ext.class": rr._class, "ext.math": rr._ext_math()}, stdout=out)
+    os.environ.setdefault("MGPOISSON_LIB", os.path.join(PKG, "libmgpoisson.so"))
+    (cls,) = it.run_file(CUDA_LUA)
+    cls.set("debugging", True)
+    obj = ml.lua_call(cls, [float(size), real])[0]
+    ml.lua_call(ml.lua_index(obj, "run"), [obj])
+    text = out.getvalue()
+    want = "#iter\terr\n"
+    for cyc in range(2):
+        for k in range(per_cycle * cyc, per_cycle * (cyc + 1)):
+            want += _show_text(names[k], g[f"t{k:05d}"], Ls[k])
+        want += f"{cyc + 1}\t"
+        assert text.startswith(want), f"cycle {cyc + 1}: dump text differs at char {next(i for i, (a, b) in enumerate(zip(text, want)) if a != b) if not text.startswith(want) else -1}"
+        rest = text[len(want):]
+        line = rest[:rest.index("\n")]
+        assert abs(float(line) - float(g["errs"][cyc])) <= 1e-12 * float(g["errs"][cyc])
+        want += line + "\n"
+    assert text == want
+    ffi.close()
+
+
+def _run_script(path, args, env):
+    ffi = minilua_ffi.FFI(search_dirs=[PKG])
+    out = io.StringIO()
+    it = ml.Interpreter(modules={"ffi": ffi.module(), "ext.class": rr._class, "ext.math": rr._ext_math()}, stdout=out,
+                        search_dirs=[os.path.join(PKG, "lua")])
+    it.modules["bit"] = it.globals.vars["bit"]
+    it.globals.vars["arg"] = ml.Interpreter.table_from({i + 1: a for i, a in enumerate(args)})
+    os.environ.setdefault("MGPOISSON_LIB", os.path.join(PKG, "libmgpoisson.so"))
+    old = {k: os.environ.get(k) for k in env}
+    os.environ.update(env)
+    try:
+        it.run_file(path)
+    finally:
+        for k, v in old.items():
+            if v is None:
+                os.environ.pop(k, None)
+            else:
+                os.environ[k] = v
+        ffi.close()
+    return out.getvalue()
+
+
+@pytest.mark.gpu
+def test_timing_driver_writes_the_reference_table(tmp_path):
+    """lua/test/test-cuda.lua: the `cpu-vs-gpu.txt` artefact of test/test.lua:16-33,45-65 with a `cuda` column."""
+    tsv = tmp_path / "cpu-vs-gpu.txt"
+    text = _run_script(os.path.join(PKG, "lua", "test", "test-cuda.lua"), ["4", "5"], {"MGPOISSON_TSV": str(tsv)})
+    lines = tsv.read_text().splitlines()
+    assert lines[0] == "#size\tcuda" and len(lines) == 3
+    for ln, size in zip(lines[1:], (16, 32)):
+        a, b = ln.split("\t")
+        assert int(a) == size and float(b) >= 0.0
+    assert "#size\tcuda" in text and "#iter\terr" in text          # echoed to the terminal, and run() printed its lines
+
+
+@pytest.mark.gpu
+def test_convergence_driver_writes_the_reference_tables(tmp_path, mgp):
+    """lua/test/converge-cuda.lua: converge/<size>.txt of test/converge-multigrid-vs-krylov.lua:79-89 -- per iteration
+    |psi|_inf of the multigrid (cpu.lua form) and |x|_inf of conjugate gradient, minus the smallest recorded value."""
+    _run_script(os.path.join(PKG, "lua", "test", "converge-cuda.lua"), ["40", "8", "16"], {"MGPOISSON_CONVERGE_DIR": str(tmp_path)})
+    for size in (8, 16):
+        rows = [ln.split("\t") for ln in (tmp_path / f"{size}.txt").read_text().splitlines()]
+        s = mgp.MultigridCUDA(size, "double", dim=2, out=False)
+        mgv = []
+        for _ in range(40):
+            s.zero_corrections()
+            e = s.step()
+            mgv.append(s.linf_norm())
+            if e < 1e-20 or not np.isfinite(e):
+                break
+        s.init_cells()
+        _, cgv = s.conjgrad(max_iter=size * size * 4, epsilon=1e-20)
+        s.close()
+        n = max(len(mgv), len(cgv))
+        assert len(rows) == n and all(len(r) == 2 for r in rows)
+        lo = min(mgv + cgv)
+        for k in range(n):
+            for col, vals in ((0, mgv), (1, cgv)):
+                cell = rows[k][col]
+                if k < len(vals):
+                    assert cell == ml.lua_tostring(vals[k] - lo), (size, k, col, cell, vals[k] - lo)
+                else:
+                    assert cell in ("nan", "-nan")
+        assert any(float(c) == 0.0 for r in rows for c in r if "nan" not in c)
