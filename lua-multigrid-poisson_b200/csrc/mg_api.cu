@@ -133,6 +133,15 @@ int mg_set_option(mg_ctx *ctx, const char *name, int value)
     else if (n == "graph") ctx->use_graph = value != 0;
     else if (n == "stream_min_L") ctx->stream_min_L = value < 64 ? 64 : value;
     else if (n == "tz") ctx->tz_override = value;
+    else if (n == "ncta") ctx->ncta_override = value < 0 ? 0 : value;
+    else if (n == "cluster_L") {   // widest level of the one-cluster kernel (0 = off); it covers at most 256
+        if (value < 0 || value > (1 << (SMALL_MAX_LEVELS - 1))) return ctx->fail(MG_EINVAL, "cluster_L must be 0..256");
+        ctx->cluster_L = value;
+    }
+    else if (n == "cluster_ctas") {
+        if (value != 0 && value != 1 && value != 2 && value != 4 && value != 8 && value != 16) return ctx->fail(MG_EINVAL, "cluster_ctas must be 0 (auto), 1, 2, 4, 8 or 16");
+        ctx->cluster_ctas = value;
+    }
     else if (n == "stream_flags") ctx->stream_flags = value;
     else if (n == "slab_p2p") {   // 0: halo planes by ncclSend/ncclRecv (or memcpy), 1: fused peer stores
         for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) {

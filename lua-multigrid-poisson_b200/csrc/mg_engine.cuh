@@ -89,6 +89,9 @@ struct mg_ctx {
     int fastdiv_opt = 1;     // fp32 streaming smoother: branch-free division kernel + guarded re-run kernel (0: guarded kernel only)
     int fast_min_L = 256;    // ... at levels at least this wide (128^3: the second launch costs what the branches cost)
     int tz_override = 0;     // planes per CTA of the streaming smoother (0 = cost model)
+    int ncta_override = 0;   // CTAs per launch of the streaming smoother (0 = one per SM); debug
+    int cluster_L = 0;       // widest level handled by the one-cluster kernel (0 = off, the default: see init)
+    int cluster_ctas = 0;    // CTAs of that cluster (0 = the widest the device schedules: 16 or 8)
     // TMA descriptors of the source fields, keyed by (pointer, level width, box x, box y)
     std::map<std::tuple<const void *, int, int, int, int>, CUtensorMap> tmaps;
     int tensor_map(const void *base, int L, int nplanes, int box_x, int box_y, const CUtensorMap **out);
@@ -434,30 +437,38 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             const long min_planes = 16;  // below this the 3*NST fill/drain steps dominate (8 measured the same)
             if (ncta > (work + min_planes - 1) / min_planes) ncta = (work + min_planes - 1) / min_planes;
         }
+        if (c->ncta_override > 0) ncta = c->ncta_override;   // debug: exercises the partitions on small grids
         if (ncta < 1) ncta = 1;
         if (ncta > work / 2) ncta = work / 2 > 0 ? work / 2 : 1;
-        // Lock-step partition ("lockstep" option, default on): when there are fewer tile columns than CTAs (but
-        // at least 70 % as many), the first `tiles` CTAs take one whole column each over the planes below zsplit
-        // and march through z together -- the halo rows and partly used sectors that neighbouring tiles share are
-        // then served by L2 instead of HBM (512^3: DRAM reads 2.2 -> 1.28 GB per pass, compulsory 1.07) -- and the
-        // other CTAs share the planes above the split in equal parts. zsplit balances the two groups: a column
-        // costs zs + OV steps, a helper CTA its planes plus OV per chunk (OV = fill/drain steps of the pipeline).
-        int zsplit = 0;
-        if (c->lockstep_opt != 0 && c->tz_override <= 0 && S >= 3 && tiles < ncta && tiles * 10 >= ncta * 7 && nown >= 32) {
+        // Lock-step partition ("lockstep" option, default on; mg_stream3d.cuh, Stream3DArgs::ncol): whole tile columns
+        // march through z together, so the halo rows and partly used sectors neighbouring tiles share are served by L2
+        // instead of HBM (512^3: DRAM reads 2.2 -> 1.28 GB per pass, compulsory 1.07).
+        //  * fewer tile columns than CTAs (but >= 70 %): every column whole below zcol, the spare CTAs share the planes
+        //    above it. zcol balances the two groups: a column costs zs + OV steps, a helper CTA its planes plus OV per
+        //    chunk (OV = fill/drain steps of the pipeline).
+        //  * more columns than CTAs (1024^2 planes: 494): whole waves of ncta columns, then the last partial wave is
+        //    dealt out in equal shares to everybody.
+        int ncol = 0, zcol = 0, rem_cta0 = 0, rem_tile0 = 0, rem_z0 = 0;
+        if (c->lockstep_opt != 0 && c->tz_override <= 0 && S >= 3 && nown >= 32) {
             const int OV = 3 * C::H - 1;
-            const long nh = ncta - tiles;
-            double bestc = 1e30;
-            for (int zs = nown; zs >= nown / 2; zs -= 2) {
-                const double planes = (double)tiles * (nown - zs) / nh;
-                const double chunks = zs == nown ? 0.0 : (double)tiles / nh + 1.0;
-                const double cost = std::max((double)(zs + OV), planes + chunks * OV);
-                if (cost < bestc) { bestc = cost; zsplit = zs; }
+            if (tiles < ncta && tiles * 10 >= ncta * 7) {
+                const long nh = ncta - tiles;
+                double bestc = 1e30;
+                int zsplit = 0;
+                for (int zs = nown; zs >= nown / 2; zs -= 2) {
+                    const double planes = (double)tiles * (nown - zs) / nh;
+                    const double chunks = zs == nown ? 0.0 : (double)tiles / nh + 1.0;
+                    const double cost = std::max((double)(zs + OV), planes + chunks * OV);
+                    if (cost < bestc) { bestc = cost; zsplit = zs; }
+                }
+                if (zsplit > 0 && zsplit < nown) { ncol = (int)tiles; zcol = zsplit; rem_cta0 = (int)tiles; rem_tile0 = 0; rem_z0 = zsplit; }
+            } else if (tiles >= ncta) {
+                ncol = (int)(tiles / ncta * ncta); zcol = nown; rem_cta0 = 0; rem_tile0 = ncol; rem_z0 = 0;
             }
-            if (zsplit >= nown) zsplit = 0;
         }
         dim3 grid((unsigned)ncta, 1, 1);
         Stream3DArgs<R> a{dst, Vp, Rout, L, c->stream_flags, nz_lo, nz_hi, zdom0, zdom0 + L, rz_off, vz_off,
-                          nullptr, nullptr, nullptr, nullptr, c->G, nullptr, nullptr, nullptr, zsplit,
+                          nullptr, nullptr, nullptr, nullptr, c->G, nullptr, nullptr, nullptr, ncol, zcol, rem_cta0, rem_tile0, rem_z0,
                           (unsigned int *)((char *)c->arena + ARENA_REDO_OFF), f};
         if (c->dist[lv] && c->p2p) {  // fused halo exchange: same offsets inside the neighbours' arenas
             const size_t doff = c->arena_off(dst);
@@ -905,11 +916,59 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         return MG_OK;
     }
 
+    // (K-d2) every level <= lv in one launch of one thread-block cluster (mg_small.cuh, k_cluster_vcycle); the levels
+    // <= small_L inside it by the cluster's first CTA alone
+    int cluster_vcycle(mg_ctx *c, double h, R *u, const R *f, int lv)
+    {
+        ClusterArgs<R, A> ca;
+        memset(&ca, 0, sizeof(ca));
+        SmallArgs<R, A> &a = ca.s;
+        a.top = lv;
+        a.smooth = c->smooth;
+        double hl = h;
+        for (int l = lv; l >= 0; --l, hl *= 2) {
+            a.u[l] = l == lv ? u : (R *)c->V[l];
+            a.f[l] = l == lv ? f : (const R *)c->R[l];
+            a.w[l] = (R *)c->W[l];
+            a.coef[l] = make_coef<A>(DIM, hl, c->omega);
+        }
+        ca.top1 = 0;
+        while ((2 << ca.top1) <= c->small_L && ca.top1 + 1 < lv) ++ca.top1;
+        auto kern = k_cluster_vcycle<R, A, DIM>;
+        if (c->cluster_ctas == 0) {   // the widest cluster the device schedules: 16 (non-portable size) or 8
+            c->cluster_ctas = 8;
+            if (cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess) {
+                cudaLaunchConfig_t q = {};
+                q.gridDim = dim3(16); q.blockDim = dim3(1024);
+                cudaLaunchAttribute qa[1];
+                qa[0].id = cudaLaunchAttributeClusterDimension;
+                qa[0].val.clusterDim.x = 16; qa[0].val.clusterDim.y = 1; qa[0].val.clusterDim.z = 1;
+                q.attrs = qa; q.numAttrs = 1;
+                int ncl = 0;
+                if (cudaOccupancyMaxActiveClusters(&ncl, kern, &q) == cudaSuccess && ncl >= 1) c->cluster_ctas = 16;
+            }
+            cudaGetLastError();
+        }
+        if (c->cluster_ctas > 8) MG_CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3((unsigned)c->cluster_ctas); cfg.blockDim = dim3(1024); cfg.stream = c->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = (unsigned)c->cluster_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        c->prof_begin(MG_K_SMALL, 1 << lv, 2 * c->smooth);
+        MG_CK(c, cudaLaunchKernelEx(&cfg, kern, ca));
+        c->prof_end();
+        MG_LAUNCH_CHECK(c);
+        return MG_OK;
+    }
+
     int twogrid_fused(mg_ctx *c, double h, void *u_, const void *f_, int lv) override
     {
         R *u = (R *)u_;
         const R *f = (const R *)f_;
         if (lv == 0 || (1 << lv) <= c->small_L) return small_vcycle(c, h, u, f, lv);
+        if ((1 << lv) <= c->cluster_L && lv < SMALL_MAX_LEVELS) return cluster_vcycle(c, h, u, f, lv);
         R *cur = u, *oth = (R *)c->W[lv];
         R *Rc = (R *)c->R[lv - 1], *Vc = (R *)c->V[lv - 1];
         int rc;
@@ -995,28 +1054,51 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         *out = *c->h_scalar;
         return MG_OK;
     }
-    // x = psi (initial guess as found, the experiment uses -f = initCells' psi), b = f
+    // x = psi (initial guess as found, the experiment uses -f = initCells' psi), b = f.
+    // Slabs (one process per GPU): every rank iterates on the planes it owns; the ghost planes of p are refreshed by
+    // ncclSend/ncclRecv before every operator application and the three scalars of an iteration are all-reduced.
     int cg(mg_ctx *c, int max_iter, double epsilon, double *err_hist, double *linf_hist, int *n_done) override
     {
-        if (c->group) return c->fail(MG_EUNSUPPORTED, "mg_cg: single-GPU only");
+        SlabGroup *g = c->group;
+        if (g && !g->nccl) return c->fail(MG_EUNSUPPORTED, "mg_cg on slabs: one process per GPU (mg_create_slab) only");
+        if (g && DIM != 3) return c->fail(MG_EUNSUPPORTED, "slab decomposition is 3-D only");
         const int top = c->nlevels - 1, L = c->size;
-        const size_t n = c->N;
-        const size_t field_bytes = (n * c->elem + 7) / 8 * 8;   // the double partials behind the field stay 8-byte aligned
-        if (!c->cg_tmp) MG_CK(c, cudaMalloc(&c->cg_tmp, field_bytes + 2 * sizeof(double) * (size_t)c->npartial + sizeof(double) * CG_NSCAL));
-        R *x = (R *)c->psi, *r = (R *)c->W[top], *p = (R *)c->psiOld, *Ap = (R *)c->cg_tmp;
-        const R *b = (const R *)c->f;
+        const size_t n = g ? c->own_elems(top) : c->N, off = g ? c->own_off_elems(top) : 0;
+        const int slab = g ? 1 : 0;
+        const size_t field_bytes = (c->Ntop * c->elem + 7) / 8 * 8;   // the double partials behind the field stay 8-byte aligned
+        if (!c->cg_tmp) {
+            MG_CK(c, cudaMalloc(&c->cg_tmp, field_bytes + 2 * sizeof(double) * (size_t)c->npartial + sizeof(double) * CG_NSCAL));
+            MG_CK(c, cudaMemsetAsync(c->cg_tmp, 0, field_bytes, c->stream));
+        }
+        R *x = (R *)c->psi + off, *r = (R *)c->W[top] + off, *p = (R *)c->psiOld + off, *Ap = (R *)c->cg_tmp + off;
+        const R *b = (const R *)c->f + off;
         double *part2 = (double *)((char *)c->cg_tmp + field_bytes), *scal = part2 + 2 * c->npartial;
         double *partA = c->d_partial, *partB = part2;
         const A inv_h2 = make_coef<A>(DIM, 1.0 / L).inv_h2;
         const int nb = c->npartial;
-        auto reduce = [&](double *part, int slot, int is_max) {
+        int rc;
+        auto reduce = [&](double *part, int slot, int is_max) -> int {
             k_cg_reduce<<<1, 1024, 0, c->stream>>>(part, nb, scal, slot, is_max);
             c->count_launch();
+            if (g) {
+                int e = g->api->AllReduce(scal + slot, scal + slot, 1, NcclApi::kFloat64, is_max ? NcclApi::kMax : NcclApi::kSum, g->comm, c->stream);
+                if (e) return c->fail(MG_ECUDA, g->api->GetErrorString(e));
+            }
+            return MG_OK;
         };
-        k_cg_init<R, A, DIM><<<nb, 256, 0, c->stream>>>(r, p, x, b, L, inv_h2, partA, partB);
+        auto ghosts = [&](const void *field) -> int {   // planes next to the slab, from the two neighbours
+            if (!g) return MG_OK;
+            const bool was = c->p2p;
+            c->p2p = false;                 // an explicit exchange, whatever the smoother's transport is
+            int e = slab_exchange(g, c->arena_off(field), top, 1, true);
+            c->p2p = was;
+            return e;
+        };
+        if ((rc = ghosts(c->psi))) return rc;
+        k_cg_init<R, A, DIM><<<nb, 256, 0, c->stream>>>(r, p, x, b, L, inv_h2, partA, partB, n, slab);
         MG_LAUNCH_CHECK(c);
-        reduce(partA, CG_RR, 0);
-        reduce(partB, CG_BB, 0);
+        if ((rc = reduce(partA, CG_RR, 0))) return rc;
+        if ((rc = reduce(partB, CG_BB, 0))) return rc;
         double h[CG_NSCAL];
         MG_CK(c, cudaMemcpyAsync(h, scal, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
         MG_CK(c, cudaStreamSynchronize(c->stream));
@@ -1025,13 +1107,14 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         double err = std::sqrt(h[CG_RR] / bb);
         if (!(err < epsilon)) {
             for (it = 1; it <= max_iter; ++it) {
-                k_cg_apply<R, A, DIM><<<nb, 256, 0, c->stream>>>(Ap, p, L, inv_h2, partA);
+                if ((rc = ghosts(c->psiOld))) return rc;
+                k_cg_apply<R, A, DIM><<<nb, 256, 0, c->stream>>>(Ap, p, L, inv_h2, partA, n, slab);
                 MG_LAUNCH_CHECK(c);
-                reduce(partA, CG_PAP, 0);
+                if ((rc = reduce(partA, CG_PAP, 0))) return rc;
                 k_cg_update<R, A><<<nb, 256, 0, c->stream>>>(x, r, p, Ap, n, scal, partA, partB);
                 MG_LAUNCH_CHECK(c);
-                reduce(partA, CG_RRNEW, 0);
-                reduce(partB, CG_XMAX, 1);
+                if ((rc = reduce(partA, CG_RRNEW, 0))) return rc;
+                if ((rc = reduce(partB, CG_XMAX, 1))) return rc;
                 MG_CK(c, cudaMemcpyAsync(h, scal, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
                 MG_CK(c, cudaStreamSynchronize(c->stream));
                 err = std::sqrt(h[CG_RRNEW] / bb);
@@ -1045,6 +1128,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             }
             if (it > max_iter) it = max_iter;
         }
+        if (g) { c->u_ghost_dirty = true; }   // psi changed behind the smoother's back: its ghosts are stale
         if (n_done) *n_done = it;
         return MG_OK;
     }
@@ -1142,6 +1226,9 @@ inline int mg_ctx::init(int dim_, int size_, int real_kind_, int smooth_, int de
     N = (size_t)size * size * (dim == 3 ? (size_t)size : 1);
     Ntop = level_elems(nlevels - 1);
     small_L = dim == 3 ? 16 : 64;
+    cluster_L = 0;   // MEASURED (512^3 fp32): with 64^3 and 32^3 in the one-cluster kernel 371 V-cycles/s against 386 with the 30 separate
+                     // launches -- 16 SMs reading L2 (the acquire of every cluster barrier empties L1) lose to 148 SMs plus launch
+                     // gaps; with 32^3 only: 385 (no change). Kept as an option ("cluster_L"), off by default.
     tb2 = real_kind == MG_REAL_F32 ? 7 : 4;  // double arithmetic: 8 pipeline stages would spill
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);

@@ -49,14 +49,16 @@ __device__ __forceinline__ double block_max(double v)
 }
 
 // r = b - A(x); p = r; partial r.r and b.b
+// Slab view (multi-GPU, 3-D): the pointers address the first OWNED plane of a z-slab, n = owned points, and the planes
+// above and below are always readable (ghost planes: the neighbour's values, or +0 outside the grid), so the z test of
+// the stencil is switched off by handing it an interior plane index.
 template <typename R, typename A, int DIM>
 __global__ void k_cg_init(R *__restrict__ r, R *__restrict__ p, const R *__restrict__ x, const R *__restrict__ b,
-                          int L, A inv_h2, double *__restrict__ part_rr, double *__restrict__ part_bb)
+                          int L, A inv_h2, double *__restrict__ part_rr, double *__restrict__ part_bb, size_t n, int slab)
 {
-    const size_t n = (size_t)L * L * (DIM == 3 ? (size_t)L : 1);
     double rr = 0, bb = 0;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
-        const int i = (int)(idx % L), j = (int)((idx / L) % L), k = DIM == 3 ? (int)(idx / ((size_t)L * L)) : 0;
+        const int i = (int)(idx % L), j = (int)((idx / L) % L), k = DIM == 3 ? (slab ? 1 : (int)(idx / ((size_t)L * L))) : 0;
         const A rv = Ar<A>::sub((A)b[idx], apply_A_point<DIM, R, A>(x, i, j, k, L, idx, inv_h2));
         r[idx] = (R)rv;
         p[idx] = (R)rv;
@@ -71,12 +73,11 @@ __global__ void k_cg_init(R *__restrict__ r, R *__restrict__ p, const R *__restr
 }
 
 template <typename R, typename A, int DIM>
-__global__ void k_cg_apply(R *__restrict__ Ap, const R *__restrict__ p, int L, A inv_h2, double *__restrict__ part)
+__global__ void k_cg_apply(R *__restrict__ Ap, const R *__restrict__ p, int L, A inv_h2, double *__restrict__ part, size_t n, int slab)
 {
-    const size_t n = (size_t)L * L * (DIM == 3 ? (size_t)L : 1);
     double acc = 0;
     for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < n; idx += (size_t)gridDim.x * blockDim.x) {
-        const int i = (int)(idx % L), j = (int)((idx / L) % L), k = DIM == 3 ? (int)(idx / ((size_t)L * L)) : 0;
+        const int i = (int)(idx % L), j = (int)((idx / L) % L), k = DIM == 3 ? (slab ? 1 : (int)(idx / ((size_t)L * L))) : 0;
         const R v = (R)apply_A_point<DIM, R, A>(p, i, j, k, L, idx, inv_h2);
         Ap[idx] = v;
         acc += (double)p[idx] * (double)v;

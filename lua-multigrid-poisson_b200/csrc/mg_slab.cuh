@@ -61,7 +61,7 @@ struct NcclApi {
     int (*AllReduce)(const void *, void *, size_t, int, int, void *, cudaStream_t) = nullptr;
     const char *(*GetErrorString)(int) = nullptr;
 
-    static constexpr int kInt8 = 0, kFloat64 = 8, kSum = 0;  // ncclInt8, ncclFloat64, ncclSum
+    static constexpr int kInt8 = 0, kFloat64 = 8, kSum = 0, kMax = 2;  // ncclInt8, ncclFloat64, ncclSum, ncclMax
 
     static NcclApi *get(std::string &err)
     {

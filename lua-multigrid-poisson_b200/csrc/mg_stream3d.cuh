@@ -352,10 +352,14 @@ template <typename R> struct Stream3DArgs {
     // neighbour has published, [48] CTAs of the current pass that are done}; hs_lo / hs_hi = the
     // neighbours' headers (null at the ends of the chain, and everywhere when hs is null).
     unsigned long long *hs, *hs_lo, *hs_hi;
-    // Lock-step partition (0 = balanced shares): the first ntiles CTAs take one whole tile column each over the
-    // owned planes [nz_lo, nz_lo + zsplit) and march through z together, so the halo rows and the partly used
-    // sectors neighbouring tiles share are served by L2; the remaining CTAs share the planes above in equal parts.
-    int zsplit;
+    // Work partition (all zero = balanced shares of the tile x plane-pair work for every CTA). Lock step: the tile
+    // columns [0, ncol) are processed WHOLE over the owned planes [nz_lo, nz_lo + zcol), CTA b taking columns b, b + grid,
+    // b + 2 grid, ...: neighbouring columns then march through z together and the halo rows and partly used sectors
+    // they share are served by L2 instead of HBM. What is left -- the tiles from rem_tile0 on, planes from nz_lo + rem_z0
+    // on -- is dealt out in equal contiguous shares to the CTAs rem_cta0 .. grid-1.
+    //   fewer tiles than CTAs : ncol = all tiles, zcol < owned planes, the spare CTAs (rem_cta0 = ncol) share the top planes
+    //   more tiles than CTAs  : ncol = whole waves of grid tiles, zcol = all planes, every CTA shares the last partial wave
+    int ncol, zcol, rem_cta0, rem_tile0, rem_z0;
     // S3_FAST / S3_RERUN: {flag "repeat this pass with the guarded code", CTA arrival counter} (zero between passes)
     unsigned int *redo;
     const R *fsrc;    // the right-hand side field itself (f planes in tensor memory are fetched by plain loads, not TMA)
@@ -985,33 +989,39 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     }
     };  // run_chunk
 
-    // Balanced persistent partition: the launch is ntiles x (owned planes / 2) plane pairs of
-    // work, dealt out in equal contiguous shares to the gridDim.x CTAs (one per SM). A share
-    // may end one tile column and begin the next; each piece is a chunk with its own halo.
-    // With zsplit > 0 the first ntiles CTAs take whole columns of the planes below the split
-    // (lock step), and only the planes above it are dealt out like that, to the other CTAs.
+    // Persistent partition: the launch is ntiles x (owned planes / 2) plane pairs of work for the gridDim.x CTAs (one
+    // per SM). A share of the balanced part may end one tile column and begin the next; each piece is a chunk with its
+    // own halo.
+    // Lock-step columns first (Stream3DArgs::ncol), then this CTA's share of the remainder.
     {
         const int ntx = (L + TX - 1) / TX, nty = (L + TY - 1) / TY, ntiles = ntx * nty;
-        int zbase = a.nz_lo, nb = (int)gridDim.x, b = (int)blockIdx.x;
-        long long npair = (a.nz_hi - a.nz_lo) >> 1, lo, hi;
-        if (a.zsplit > 0 && b < ntiles) {           // one whole column below the split
-            npair = a.zsplit >> 1;
-            lo = npair * b; hi = lo + npair;
-        } else {
-            if (a.zsplit > 0) { zbase += a.zsplit; npair -= a.zsplit >> 1; b -= ntiles; nb -= ntiles; }
-            const long long W2 = (long long)ntiles * npair;
-            lo = W2 * b / nb; hi = W2 * (b + 1) / nb;
+        const int nb = (int)gridDim.x, b = (int)blockIdx.x;
+        int col = b;                                   // next whole column of this CTA
+        long long lo = 0, hi = 0, npair = 1;           // its share of the remainder, in plane pairs
+        const int zrem = a.nz_lo + a.rem_z0;
+        if (b >= a.rem_cta0) {
+            npair = (a.nz_hi - zrem) >> 1;
+            const long long W2 = (long long)(ntiles - a.rem_tile0) * npair;
+            lo = W2 * (b - a.rem_cta0) / (nb - a.rem_cta0);
+            hi = W2 * (b - a.rem_cta0 + 1) / (nb - a.rem_cta0);
         }
-        while (lo < hi) {
-            const long long tile = lo / npair, zp = lo - tile * npair;
-            const long long n = min(npair - zp, hi - lo);
-            if (!skip) run_chunk((int)(tile % ntx) * TX, (int)(tile / ntx) * TY, zbase + 2 * (int)zp, zbase + 2 * (int)(zp + n));
-            lo += n;
+        while (true) {
+            int tile, z0, z1;
+            if (col < a.ncol) {
+                tile = col; z0 = a.nz_lo; z1 = a.nz_lo + a.zcol;
+                col += nb;
+            } else if (lo < hi) {
+                const long long tl = lo / npair, zp = lo - tl * npair;
+                const long long n = min(npair - zp, hi - lo);
+                tile = a.rem_tile0 + (int)tl; z0 = zrem + 2 * (int)zp; z1 = zrem + 2 * (int)(zp + n);
+                lo += n;
+            } else {
+                break;
+            }
+            if (!skip) run_chunk((tile % ntx) * TX, (tile / ntx) * TY, z0, z1);
         }
     }
 
-    // The last CTA of the pass publishes "pass n+1 done" to both neighbours: all our stores,
-    // local and into their ghost planes, are ordered before it.
     if (FT && !skip) {   // every tcgen05.ld was awaited by its consumer
         tmem_fence_before_sync();
         __syncthreads();

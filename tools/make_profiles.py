@@ -6,8 +6,9 @@
 
   config: 3d_512_float (default) | 2d_4096_float | 2d_2048_double -- the bench.py configuration the capture ran
   * <launches.csv>: `ncu --metrics gpu__time_duration.sum --clock-control none -c N --csv --log-file ... python bench.py ...`
-  * <full.ncu-rep>: `ncu --set full --clock-control none --import-source on -k regex:'k_stream3d|k_warp2d|k_small' -c N ...`
-    of the FIRST V-cycle(s) bench.py runs (warm-up); launches are matched, in order, with the pass schedule of a cycle.
+  * `full` takes the metrics CSV of the FIRST V-cycle bench.py runs (`ncu --metrics <METRICS below> -k regex:'k_stream3d|k_warp2d|k_small'
+    -c N --csv --log-file m.csv ...`); launches are matched, in order, with the pass schedule of a cycle. A `--set full
+    --import-source on` capture of the dominant kernel next to it (prof_<tag>_<config>_top.ncu-rep) adds the source-level summary.
 `full` writes profiles/<tag>_ncu_full_<config>.md and merges DRAM bytes per launch into profiles/dram_traffic.json,
 which bench.py reads for `roofline.traffic` / `roofline.frac`.
 """
@@ -40,20 +41,13 @@ def launches(path, tag, config):
     hdr = rows[0]
     iname, ival, igrid, iblock = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Grid Size"), hdr.index("Block Size")
     recs = [(short(r[iname]), r[igrid], r[iblock], float(r[ival].replace(",", ""))) for r in rows[1:]]
-    # one V-cycle = from one launch of the first pass kernel of the cycle to the next
-    first = recs[[i for i, r in enumerate(recs) if r[0].startswith(("k_stream3d", "k_warp2d", "k_small"))][0]]
-    starts = [i for i, r in enumerate(recs) if r[:3] == first[:3]]
-    # the same kernel may appear twice per cycle: take the period as the distance between equal whole sequences
-    period = None
-    for cand in range(1, len(starts)):
-        p = starts[cand] - starts[0]
-        if starts[0] + 2 * p <= len(recs) and [r[0] for r in recs[starts[0]:starts[0] + p]] == [r[0] for r in recs[starts[0] + p:starts[0] + 2 * p]]:
-            period = p
-            break
-    if period is None:
-        period = len(recs) - starts[0]
-    a = starts[0] + period       # second cycle (warm)
-    cyc = recs[a:a + period] if a + period <= len(recs) else recs[starts[0]:starts[0] + period]
+    # one V-cycle = the launches between two consecutive launches of the one-CTA small-level kernel (the bottom of the
+    # V): the second half of one cycle and the first half of the next -- the same multiset of launches as one cycle
+    smalls = [i for i, r in enumerate(recs) if r[0].startswith(("k_small_vcycle", "k_cluster_vcycle"))]
+    if len(smalls) >= 3:
+        cyc = recs[smalls[1]:smalls[2]]
+    else:
+        cyc = recs
     tot = sum(t for *_, t in cyc)
     agg = collections.OrderedDict()
     for n, g, bk, t in cyc:
@@ -101,61 +95,84 @@ def schedule(config):
     return dim, size, real, order
 
 
+def read_metrics_csv(path):
+    """`ncu --metrics a,b,c --csv --log-file X`: one row per (launch, metric). Returns [(kernel name, {metric: SI value})]."""
+    rows = list(csv.reader(l for l in open(path) if l.startswith('"')))
+    hdr = rows[0]
+    ix = {h: i for i, h in enumerate(hdr)}
+    out = collections.OrderedDict()
+    for r in rows[1:]:
+        key = r[ix["ID"]]
+        e = out.setdefault(key, {"name": short(r[ix["Kernel Name"]]), "grid": r[ix["Grid Size"]], "block": r[ix["Block Size"]], "m": {}})
+        try:
+            e["m"][r[ix["Metric Name"]]] = float(r[ix["Metric Value"]].replace(",", "")) * SCALE.get(r[ix["Metric Unit"]], 1)
+        except ValueError:
+            pass
+    return list(out.values())
+
+
+METRICS = ("dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration.sum,smsp__issue_active.avg.pct_of_peak_sustained_active,"
+           "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum,l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum,sm__cycles_elapsed.max,"
+           "launch__registers_per_thread,sm__warps_active.avg.pct_of_peak_sustained_active,lts__t_sector_hit_rate.pct,"
+           "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed,smsp__inst_executed.sum")
+
+
 def full(rep, tag, config):
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
-    rows = list(csv.reader(raw.splitlines()))
-    hdr, units = rows[0], rows[1]
-
-    def val(r, w):
-        i = hdr.index(w)
-        return float(r[i].replace(",", "")) * SCALE.get(units[i], 1)
-
+    """rep = the metrics CSV of the first V-cycle (`ncu --metrics <METRICS> --csv --log-file ...`)"""
+    launches_ = read_metrics_csv(rep)
     dim, size, real, order = schedule(config)
     elem = 8 if real == "double" else 4
     data = []
-    for r in rows[2:]:
-        kn = short(r[hdr.index("Kernel Name")])
+    for e in launches_:
+        kn = e["name"]
         if kn.startswith("k_stream3d"):
             a = [x.strip() for x in kn[kn.index("<") + 1:-1].split(",")]
             if len(a) >= 8 and a[7] == "2":
                 continue   # the (empty) guarded re-run kernel behind every branch-free pass
-        if kn.startswith(("k_stream3d", "k_warp2d", "k_small")):
-            data.append((kn, r))
+        if kn.startswith(("k_stream3d", "k_warp2d", "k_small", "k_cluster")):
+            data.append(e)
     lines = [f"| launch | kernel | grid x block | time (ncu, cold) | DRAM read + write | compulsory | DRAM / compulsory | DRAM GB/s (% of {PEAK:.1f}) | "
-             "issue slots busy | regs | smem wavefronts (conflict replays) | LSU-smem busy |", "|---|---|---|---|---|---|---|---|---|---|---|---|"]
+             "issue slots busy | regs | smem wavefronts (conflict replays) | LSU-smem busy | L2 hit |", "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
     traffic = {}
     c = 2.0 ** -dim
-    for (kind, L, sw), (kn, r) in zip(order, data):
+    for (kind, L, sw), e in zip(order, data):
         name = f"{kind}[L={L},sweeps={sw}]"
-        rd, wr, t = val(r, "dram__bytes_read.sum"), val(r, "dram__bytes_write.sum"), val(r, "gpu__time_duration.sum")
-        wf = val(r, "l1tex__data_pipe_lsu_wavefronts_mem_shared.sum")
-        bc = val(r, "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum")
-        cyc = val(r, "sm__cycles_elapsed.max")
+        m, kn = e["m"], e["name"]
+        rd, wr, t = m.get("dram__bytes_read.sum", 0), m.get("dram__bytes_write.sum", 0), m.get("gpu__time_duration.sum", 1)
+        wf = m.get("l1tex__data_pipe_lsu_wavefronts_mem_shared.sum", 0)
+        bc = m.get("l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum", 0)
+        cyc = m.get("sm__cycles_elapsed.max", 1)
         if kind == "small_levels":
             comp = sum((6 + 2 * c) * float(l) ** dim for l in [L >> k for k in range(20)] if l > 1) * elem
         else:
             comp = (3 + (c if "+" in kind else 0)) * elem * float(L) ** dim
-        lines.append(f"| `{name}` | `{kn[:kn.index('<') + 40]}...` | {r[hdr.index('launch__grid_size')]} x {r[hdr.index('launch__block_size')]} | {t * 1e3:.4f} ms | "
+        lines.append(f"| `{name}` | `{kn[:kn.index('<') + 34] if '<' in kn else kn}...` | {e['grid']} x {e['block']} | {t * 1e3:.4f} ms | "
                      f"{rd / 1e9:.3f} + {wr / 1e9:.3f} GB | {comp / 1e9:.3f} GB | {(rd + wr) / comp:.2f} | "
                      f"{(rd + wr) / t / 1e9:.0f} ({(rd + wr) / t / 1e9 / PEAK * 100:.0f} %) | "
-                     f"{float(r[hdr.index('smsp__issue_active.avg.pct_of_peak_sustained_active')]):.1f} % | "
-                     f"{r[hdr.index('launch__registers_per_thread')]} | {wf / 1e6:.1f} M ({100 * bc / max(wf, 1):.1f} %) | "
-                     f"{100 * wf / 148 / cyc:.0f} % |")
+                     f"{m.get('smsp__issue_active.avg.pct_of_peak_sustained_active', 0):.1f} % | "
+                     f"{int(m.get('launch__registers_per_thread', 0))} | {wf / 1e6:.1f} M ({100 * bc / max(wf, 1):.1f} %) | "
+                     f"{100 * wf / 148 / cyc:.0f} % | {m.get('lts__t_sector_hit_rate.pct', 0):.0f} % |")
         traffic[name] = rd + wr
-    src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
-    tmp = "/tmp/_src_page.csv"
-    open(tmp, "w").write(src)
-    summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_src_summary.py"), tmp, "12"],
-                          capture_output=True, text=True).stdout
+    summ = ""
+    srcrep = os.path.join(os.path.dirname(rep), f"prof_{tag}_{config}_top.ncu-rep")
+    if not os.path.exists(srcrep):
+        srcrep = None
+    if srcrep:
+        src = subprocess.run(["ncu", "-i", srcrep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+        tmp = "/tmp/_src_page.csv"
+        open(tmp, "w").write(src)
+        summ = subprocess.run([sys.executable, os.path.join(ROOT, "tools", "ncu_src_summary.py"), tmp, "12"],
+                              capture_output=True, text=True).stdout
     head = [f"# ncu --set full capture of the fused passes of one V-cycle: {config} ({tag})", "",
             "Command (on a B200, right after the same command exited 0 without ncu):", "", "```",
-            "ncu --set full --clock-control none --import-source on -k regex:'k_stream3d|k_warp2d|k_small' -c N -o prof \\",
-            "    python bench.py [--config ...] --steps 3 --warmup 3 --no-cpu", "```", "",
+            "ncu --metrics <tools/make_profiles.py METRICS> --clock-control none -k regex:'k_stream3d|k_warp2d|k_small' -c N --csv --log-file m.csv \\",
+            "    python bench.py [--config ...] --steps 3 --warmup 3 --no-cpu",
+            "ncu --set full --clock-control none --import-source on -k regex:<top kernel> -c 1 -o prof_top ...   (source-level summary below)", "```", "",
             "DRAM = dram__bytes_read.sum + dram__bytes_write.sum of the launch; compulsory = what the fused launch cannot avoid",
             "(read u and f, write u, + the coarse field it reads or writes). The (empty) guarded re-run kernels that follow the",
             "branch-free fp32 passes are left out. Times under ncu are cold-cache and serialised.", ""]
-    tail = ["", "## Source-level summary of the first launch (`ncu --page source`, tools/ncu_src_summary.py)", "", "```"] + \
-        summ.splitlines() + ["```", ""]
+    tail = (["", "## Source-level summary of the dominant launch (`ncu --set full --import-source on`, `--page source`, tools/ncu_src_summary.py)", "", "```"] +
+            summ.splitlines() + ["```", ""]) if summ else []
     note_path = os.path.join(ROOT, "profiles", f"{tag}_ncu_reading_{config}.md")
     note = open(note_path).read().splitlines() if os.path.exists(note_path) else []
     open(os.path.join(ROOT, "profiles", f"{tag}_ncu_full_{config}.md"), "w").write("\n".join(head + lines + [""] + note + tail))

@@ -112,7 +112,10 @@ static float run_pass(int L, float *dst, const float *src, const float *f, const
     if (zs > 0 && (ntiles >= ncta || zs >= L)) zs = 0;
     zs &= ~1;
     *zs_used = zs;
-    Stream3DArgs<float> a{dst, Vp, Rout, L, g_flags, 0, L, 0, L, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, zs, g_redo, f};
+    int ncol = 0, zcol = 0, rem_cta0 = 0, rem_tile0 = 0, rem_z0 = 0;
+    if (zs > 0) { ncol = ntiles; zcol = zs; rem_cta0 = ntiles; rem_z0 = zs; }
+    else if (g_zsplit != 0 && ntiles >= ncta) { ncol = (int)(ntiles / ncta * ncta); zcol = L; rem_tile0 = ncol; *zs_used = -ncol; }
+    Stream3DArgs<float> a{dst, Vp, Rout, L, g_flags, 0, L, 0, L, 0, 0, nullptr, nullptr, nullptr, nullptr, 0, nullptr, nullptr, nullptr, ncol, zcol, rem_cta0, rem_tile0, rem_z0, g_redo, f};
     const Coef<float> cf = make_coef<float>(3, 1.0 / L);
     cudaEvent_t e0, e1;
     CK(cudaEventCreate(&e0)); CK(cudaEventCreate(&e1));

@@ -23,8 +23,10 @@ CONFIGS = [  # (dim, size, check interval)
 ]
 
 
-def solve_gpu(pkg, dim, size, tol, check, max_cycles):
+def solve_gpu(pkg, dim, size, tol, check, max_cycles, omega=1.0, rezero=True):
     s = pkg.MultigridCUDA(size, "double", dim=dim, out=False)
+    if omega != 1.0:
+        s.set_omega(omega)      # NOT the reference: weighted Jacobi, a labelled extension (mg_set_omega)
     r0 = s.residual_norm()
     s.zero_corrections(); s.vcycle(); s.residual_norm()      # warm-up: graph capture, first launches
     s.init_cells()
@@ -32,7 +34,8 @@ def solve_gpu(pkg, dim, size, tol, check, max_cycles):
     c, r = 0, r0
     while c < max_cycles:
         for _ in range(check):
-            s.zero_corrections()
+            if rezero:
+                s.zero_corrections()
             s.vcycle()
         c += check
         r = s.residual_norm()                                 # synchronises: 8-byte readback
@@ -72,19 +75,25 @@ def main():
     ap.add_argument("--max-cycles", type=int, default=400000)
     ap.add_argument("--max-points", type=int, default=1 << 40)
     ap.add_argument("--threads", type=int, default=os.cpu_count() or 1)
+    ap.add_argument("--omega", type=float, default=1.0, help="relaxation weight (1 = the reference; anything else is an extension)")
+    ap.add_argument("--keep-corrections", action="store_true", help="cpu-raw.lua form: coarse corrections carried over between cycles")
     a = ap.parse_args()
     if a.oracle:
         import oracle as O
     else:
         from __graft_entry__ import load_package
         pkg = load_package()
-    for dim, size, check in CONFIGS:
+    configs = CONFIGS if a.omega == 1.0 else [(2, 64, 1), (2, 256, 1), (2, 2048, 1), (3, 64, 1), (3, 128, 1), (3, 256, 1), (3, 512, 1)]
+    for dim, size, check in configs:
         if size ** dim > a.max_points:
             continue
         r = solve_oracle(O, dim, size, a.tol, check, a.max_cycles, a.threads) if a.oracle else \
-            solve_gpu(pkg, dim, size, a.tol, check, a.max_cycles)
-        r.update({"dim": dim, "size": size, "real": "double", "tol": a.tol, "check_every": check,
-                  "variant": "cpu.lua (coarse corrections re-zeroed every cycle)", "impl": "oracle" if a.oracle else "cuda"})
+            solve_gpu(pkg, dim, size, a.tol, check, a.max_cycles if a.omega == 1.0 else min(a.max_cycles, 2000), a.omega, not a.keep_corrections)
+        r.update({"dim": dim, "size": size, "real": "double", "tol": a.tol, "check_every": check, "omega": a.omega,
+                  "variant": ("cpu.lua (coarse corrections re-zeroed every cycle)" if not a.keep_corrections else
+                              "cpu-raw.lua (coarse corrections carried over)") + ("" if a.omega == 1.0 else
+                              f"; NON-REFERENCE smoother: weighted Jacobi omega = {a.omega:.6g}, one-sweep-per-launch kernels"),
+                  "impl": "oracle" if a.oracle else "cuda"})
         r["ms_per_cycle"] = 1e3 * r["seconds"] / max(r["cycles"], 1)
         print(json.dumps(r), flush=True)
 
