@@ -1,7 +1,7 @@
 // mg_ops_ref.cuh -- one kernel per reference operator (MG_MODE_REFSEQ and the per-operator
 // C-ABI entry points). One thread per cell, x fastest => coalesced rows; neighbour reuse is
 // left to L1/L2. These are the parity anchors, not the fast path (see mg_stream3d.cuh,
-// mg_tile2d.cuh, mg_small.cuh for that).
+// mg_warp2d.cuh, mg_small.cuh for that).
 #pragma once
 #include "mg_math.cuh"
 

@@ -19,8 +19,10 @@
 //           so there is no separate exchange step at all. The per-pass handshake is inside the
 //           kernel too: every CTA acquires the neighbours' "passes done" counters before its
 //           first TMA load, the last CTA to finish publishes ours (mg_stream3d.cuh, Stream3DArgs::hs).
-//           NCCL is left with the all-gather of the first replicated level, the error all-reduce
-//           and the ghost refresh after initCells / an upload.
+//           The kernel that restricts into the first replicated level stores into EVERY rank's copy of it (the
+//           all-gather, fused), framed by the epoch kernels below; NCCL is left with the error / residual
+//           all-reduce, the ghost refresh after initCells / an upload and the CG comparator: no NCCL call inside
+//           a V-cycle, which is replayed from one CUDA graph.
 //   NCCL  : (option slab_p2p = 0) ncclSend/ncclRecv of the halo planes before every pass.
 //           libnccl is dlopen()ed, so single-GPU users (LuaJIT) do not need it.
 //   MULTI : one process, one GPU per slab (mg_create_slab_multi): the same fused kernels and handshakes as FUSED, peer
@@ -29,8 +31,9 @@
 //   LOCAL : all slabs in one process on one device and one stream (peer pointers are plain
 //           pointers; slab_p2p = 0 uses cudaMemcpyAsync). This is how the slab index arithmetic
 //           and the fused stores are tested on a single GPU.
-// Measured on 8 x B200, 1024^3 fp32 (profiles/): 1733 units/s vs 261 on one GPU of the same box
-// = 83 % parallel efficiency (NCCL send/recv: 1324 = 60 %; fused + separate handshake kernels: 68 %).
+// Measured on B200s, 1024^3 fp32 (profiles/r2_bench_n*): 868 / 1568 / 2462 units/s on 2 / 4 / 8 GPUs vs 387 on one GPU
+// of the same box = efficiency 1.12 / 1.01 / 0.795 (round 1, slower single-GPU kernel: 1733 vs 261 = 0.83 at 8;
+// NCCL send/recv then: 1324; fused + separate handshake kernels: 1400). DESIGN.md section 7 has the breakdown.
 #pragma once
 #include <cuda_runtime.h>
 #include <dlfcn.h>
