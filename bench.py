@@ -543,6 +543,8 @@ def run_ours(args):
               "dram_frac_of_measured": (cyc_traffic / (ms_per_step * 1e-3) / 1e9 / peak) if cyc_traffic else None,
               "breakdown_ms": {f"{k}[L={L},sweeps={sw}]x{g['n']}": round(g["ms"], 4)
                                for (k, L, sw), g in sorted(groups.items(), key=lambda kv: -kv[1]["ms"])[:8]},
+              "breakdown_all_ms": {f"{k}[L={L},sweeps={sw}]x{g['n']}": round(g["ms"], 4)
+                                   for (k, L, sw), g in sorted(groups.items(), key=lambda kv: (-kv[0][1], kv[0][0], kv[0][2]))},
               "profiled_sum_ms": total_prof}
 
     # ---- end to end through the C ABI with HOST buffers (pinned), copies inside the timing

@@ -151,6 +151,9 @@ int mg_set_option(mg_ctx *ctx, const char *name, int value)
         }
     }
     else if (n == "lockstep") ctx->lockstep_opt = value;
+    else if (n == "small_smem") { for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) { m->small_smem_opt = value; m->drop_graph(); } }
+    else if (n == "pdl") { for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) { m->pdl_opt = value != 0; m->drop_graph(); } }
+    else if (n == "colparts") { for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) m->colparts_opt = value; }
     else if (n == "fastdiv") ctx->fastdiv_opt = value;
     else if (n == "fast_min_L") ctx->fast_min_L = value;
     else if (n == "slab_graph") ctx->slab_graph_opt = value != 0;

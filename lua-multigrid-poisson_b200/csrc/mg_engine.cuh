@@ -82,12 +82,19 @@ struct mg_ctx {
     int ty_override = 0;     // 2-D: rows per warp work item (0 = cost model)
     int stream_min_L = 128;  // smallest level width handled by the streaming (TMA) smoother
     int num_sms = 148;       // SM count of the device (queried at init)
+    int small_smem_opt = 1;  // levels <= small_L by the shared-memory one-CTA kernel (0: the global-memory walker)
+    int pdl_opt = 0;         // kernels of a V-cycle launched with programmatic stream serialization (mg_math.cuh, pdl_enter).
+                             // MEASURED (round 2, same box): 512^3 fp32 397.1 -> 393.3 V-cycles/s, 2-D 4096^2 fp32 and 2048^2 fp64
+                             // 4-5 % slower (with the faster small-level kernel in the same build): the early-scheduled CTAs of
+                             // the next kernel buy nothing here (big kernels fill every SM with one CTA; small ones are ~2 us) and the
+                             // programmatic graph edges cost more than plain ones. Off; bit-identical either way (tests).
+    int colparts_opt = 1;    // deep passes: tile columns cut into k equal z-parts when that beats equal shares for every SM
     int lockstep_opt = 1;    // lock-step partition of the streaming smoother: whole columns below zsplit + helper CTAs above
     int tma_promo = 0;       // L2 promotion of the TMA descriptors: 0 none (least DRAM over-fetch), 1 64 B, 2 128 B, 3 256 B
     int stream_flags = 0;    // debug switches of the streaming smoother (see Stream3DArgs::flags)
     double omega = 1.0;      // relaxation weight of the Jacobi smoother: 1 = the reference (mg_set_omega)
     int fastdiv_opt = 1;     // fp32 streaming smoother: branch-free division kernel + guarded re-run kernel (0: guarded kernel only)
-    int fast_min_L = 256;    // ... at levels at least this wide (128^3: the second launch costs what the branches cost)
+    int fast_min_L = 128;    // ... at levels at least this wide (128^3: 176 -> 157 us per level visit, measured in round 2)
     int tz_override = 0;     // planes per CTA of the streaming smoother (0 = cost model)
     int ncta_override = 0;   // CTAs per launch of the streaming smoother (0 = one per SM); debug
     int cluster_L = 0;       // widest level handled by the one-cluster kernel (0 = off, the default: see init)
@@ -242,6 +249,20 @@ static inline dim3 block_for(int L)
         if (e_ != cudaSuccess) return (c)->fail_cuda(e_, "kernel launch"); \
         (c)->count_launch();                                 \
     } while (0)
+
+// Launch of a V-cycle kernel (every one of them starts with pdl_enter()): with the "pdl" option the launch carries
+// cudaLaunchAttributeProgrammaticStreamSerialization, which also survives stream capture as a programmatic graph edge.
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(mg_ctx *c, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = c->pdl_opt ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 template <typename R, typename A, int DIM> struct EngineT : Engine {
     // ------------------------------------------------------------ reference operators
@@ -431,11 +452,25 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
                 if (best < 0 || cost < best) { best = cost; ncta = n; }
             }
         } else {
-            // Deep passes are issue-bound: equal shares of the tile x plane work for every
-            // resident CTA (a share may span two tile columns), no tail wave.
-            ncta = (long)c->num_sms * occ;
-            const long min_planes = 16;  // below this the 3*NST fill/drain steps dominate (8 measured the same)
-            if (ncta > (work + min_planes - 1) / min_planes) ncta = (work + min_planes - 1) / min_planes;
+            // Deep passes: one CTA per SM, no tail wave. A share of `pl` planes costs pl + OV steps per chunk it touches
+            // (OV = 3 NST - 1 fill/drain steps of the pipeline). Candidates: equal shares of the whole tile x plane work
+            // for every SM (a share that does not line up with the columns touches two of them), or every column cut into
+            // k equal parts with k x tiles CTAs -- the parts then line up, march through z together (halo rows shared
+            // through L2) and cost nown / k + OV. 256^3: 35 columns x 4 parts = 140 CTAs; the 64- and 32-plane slabs of the
+            // 8-GPU run: 130 whole columns, 35 x 4 parts of 8 planes.
+            const long nsm = (long)c->num_sms * occ;
+            const double OV = 3 * C::H - 1;
+            const double pl = (double)work / nsm;
+            double best = pl + (std::floor(pl / nown) + 2.0) * OV;
+            ncta = nsm;
+            // (The parts need not be equal: with k x tiles CTAs the kernel's balanced shares of the plane PAIRS line up with
+            // the column ends, and inside a column they differ by at most one pair. 128^3: 12 columns x 12 parts of 5-6 pairs.)
+            const long npair = nown / 2;
+            for (long k = 1; c->colparts_opt != 0 && k * tiles <= nsm && k <= npair; ++k) {
+                if (npair / k < 2) continue;
+                const double cst = 2.0 * (double)((npair + k - 1) / k) + OV;
+                if (cst < best) { best = cst; ncta = k * tiles; }
+            }
         }
         if (c->ncta_override > 0) ncta = c->ncta_override;   // debug: exercises the partitions on small grids
         if (ncta < 1) ncta = 1;
@@ -499,10 +534,10 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             }
         }
         c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : (RES ? MG_K_SWEEP_RESTRICT : MG_K_SWEEP), L, S);
-        kern<<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(*map, *fmap, a, cf);
+        MG_CK(c, launch_k(c, kern, grid, dim3(C::NTHREADS), C::SMEM_BYTES, *map, *fmap, a, cf));
         if (kern2) {
             MG_LAUNCH_CHECK(c);
-            kern2<<<grid, C::NTHREADS, C::SMEM_BYTES, c->stream>>>(*map, *fmap, a, cf);
+            MG_CK(c, launch_k(c, kern2, grid, dim3(C::NTHREADS), C::SMEM_BYTES, *map, *fmap, a, cf));
         }
         c->prof_end();
         MG_LAUNCH_CHECK(c);
@@ -785,7 +820,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         TY &= ~1;
         const int nitems = nstrips * ((L + TY - 1) / TY);
         c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : (RES ? MG_K_SWEEP_RESTRICT : MG_K_SWEEP), L, S);
-        k_warp2d<R, A, S, PRO, RES><<<(nitems + 3) / 4, 128, 0, c->stream>>>(dst, src, f, Vp, Rout, L, TY, nstrips, nitems, cf);
+        MG_CK(c, launch_k(c, k_warp2d<R, A, S, PRO, RES>, dim3((unsigned)((nitems + 3) / 4)), dim3(128), 0, dst, src, f, Vp, Rout, L, TY, nstrips, nitems, cf));
         c->prof_end();
         MG_LAUNCH_CHECK(c);
         return MG_OK;
@@ -833,16 +868,16 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         for (int s = 0; s < n; ++s) {
             c->prof_begin(s == 0 && Vp ? MG_K_SWEEP_PROLONG : MG_K_SWEEP, L, 1);
             if (s == 0 && Vp)
-                k_sweep_pp<R, A, DIM, true><<<g, b, 0, c->stream>>>(oth, cur, f, Vp, L, cf);
+                MG_CK(c, launch_k(c, k_sweep_pp<R, A, DIM, true>, g, b, 0, oth, (const R *)cur, f, Vp, L, cf));
             else
-                k_sweep_pp<R, A, DIM, false><<<g, b, 0, c->stream>>>(oth, cur, f, nullptr, L, cf);
+                MG_CK(c, launch_k(c, k_sweep_pp<R, A, DIM, false>, g, b, 0, oth, (const R *)cur, f, (const R *)nullptr, L, cf));
             c->prof_end();
             MG_LAUNCH_CHECK(c);
             R *t = cur; cur = oth; oth = t;
         }
         if (n == 0 && Vp) {
             c->prof_begin(MG_K_PROLONG_ADD, L, 0);
-            k_prolong_add<R, A, DIM><<<g, b, 0, c->stream>>>(cur, Vp, L);
+            MG_CK(c, launch_k(c, k_prolong_add<R, A, DIM>, g, b, 0, cur, Vp, L));
             c->prof_end();
             MG_LAUNCH_CHECK(c);
         }
@@ -850,7 +885,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             const int L2 = L / 2;
             dim3 b2 = block_for(L2), g2 = grid_for(DIM, L2, b2);
             c->prof_begin(MG_K_RESID_RESTRICT, L, 0);
-            k_residual_restrict<R, A, DIM><<<g2, b2, 0, c->stream>>>(Rout, f, cur, L, cf);
+            MG_CK(c, launch_k(c, k_residual_restrict<R, A, DIM>, g2, b2, 0, Rout, f, (const R *)cur, L, cf));
             c->prof_end();
             MG_LAUNCH_CHECK(c);
         }
@@ -910,7 +945,17 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         size_t n = c->level_elems(lv);
         int threads = n >= 1024 ? 1024 : (n >= 256 ? 256 : 64);
         c->prof_begin(MG_K_SMALL, 1 << lv, 2 * c->smooth);
-        k_small_vcycle<R, A, DIM><<<1, threads, 0, c->stream>>>(a);
+        // the whole sub-hierarchy in shared memory (mg_small.cuh, K-d3) when it fits; else the global-memory walker
+        const size_t sm_bytes = small_smem_bytes<DIM>(lv, sizeof(R));
+        if (c->small_smem_opt != 0 && lv <= SmallSmemMax<DIM>::LG && sm_bytes <= 227 * 1024) {
+            auto kern = k_small_vcycle_smem<R, A, DIM>;
+            MG_CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_bytes));
+            MG_CK(c, launch_k(c, kern, dim3(1), dim3((unsigned)small_team(DIM, lv)), sm_bytes, a));
+            c->prof_end();
+            MG_LAUNCH_CHECK(c);
+            return MG_OK;
+        }
+        MG_CK(c, launch_k(c, k_small_vcycle<R, A, DIM>, dim3(1), dim3((unsigned)threads), 0, a));
         c->prof_end();
         MG_LAUNCH_CHECK(c);
         return MG_OK;
@@ -952,10 +997,12 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         if (c->cluster_ctas > 8) MG_CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1));
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3((unsigned)c->cluster_ctas); cfg.blockDim = dim3(1024); cfg.stream = c->stream;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = (unsigned)c->cluster_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = c->pdl_opt ? 2 : 1;
         c->prof_begin(MG_K_SMALL, 1 << lv, 2 * c->smooth);
         MG_CK(c, cudaLaunchKernelEx(&cfg, kern, ca));
         c->prof_end();

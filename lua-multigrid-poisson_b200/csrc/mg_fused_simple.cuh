@@ -26,6 +26,7 @@ template <typename R, typename A, int DIM, bool PROLONG>
 __global__ void k_sweep_pp(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f,
                            const R *__restrict__ V, int L, Coef<A> c)
 {
+    pdl_enter();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = blockIdx.y * blockDim.y + threadIdx.y;
     int k = DIM == 3 ? blockIdx.z : 0;
@@ -56,6 +57,7 @@ __global__ void k_sweep_pp(R *__restrict__ dst, const R *__restrict__ src, const
 template <typename R, typename A, int DIM>
 __global__ void k_prolong_add(R *__restrict__ u, const R *__restrict__ V, int L)
 {
+    pdl_enter();
     int i = blockIdx.x * blockDim.x + threadIdx.x;
     int j = blockIdx.y * blockDim.y + threadIdx.y;
     int k = DIM == 3 ? blockIdx.z : 0;
@@ -70,6 +72,7 @@ template <typename R, typename A, int DIM>
 __global__ void k_residual_restrict(R *__restrict__ Rc, const R *__restrict__ f,
                                     const R *__restrict__ u, int L, Coef<A> c)
 {
+    pdl_enter();
     const int L2 = L >> 1;
     int I = blockIdx.x * blockDim.x + threadIdx.x;
     int J = blockIdx.y * blockDim.y + threadIdx.y;

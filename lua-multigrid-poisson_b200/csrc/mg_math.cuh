@@ -23,6 +23,16 @@
 
 namespace mg {
 
+// Programmatic dependent launch (the "pdl" option, mg_engine.cuh launch_k): the kernels of a V-cycle are launched with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so the next kernel's CTAs are scheduled while this one still runs
+// (PREEXIT) and block here (ACQBULK) until every prerequisite grid has completed and its writes are visible. First
+// statement of every such kernel: nothing above it may touch global memory. Without the launch attribute both
+// instructions do nothing.
+__device__ __forceinline__ void pdl_enter()
+{
+    asm volatile("griddepcontrol.launch_dependents;\n\tgriddepcontrol.wait;" ::: "memory");
+}
+
 template <typename A> struct Ar;
 template <> struct Ar<float> {
     static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }

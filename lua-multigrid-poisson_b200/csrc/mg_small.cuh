@@ -122,6 +122,7 @@ template <typename R, typename A, int DIM> __device__ void small_vcycle_body(con
 template <typename R, typename A, int DIM>
 __global__ void __launch_bounds__(1024, 1) k_cluster_vcycle(ClusterArgs<R, A> ca)
 {
+    pdl_enter();
     const SmallArgs<R, A> &a = ca.s;
     const unsigned me = cluster_cta_rank(), nc = cluster_num_ctas();
     const int t0 = (int)(me * blockDim.x + threadIdx.x), tn = (int)(nc * blockDim.x);
@@ -170,6 +171,7 @@ __global__ void __launch_bounds__(1024, 1) k_cluster_vcycle(ClusterArgs<R, A> ca
 template <typename R, typename A, int DIM>
 __global__ void __launch_bounds__(1024, 1) k_small_vcycle(SmallArgs<R, A> a)
 {
+    pdl_enter();
     small_vcycle_body<R, A, DIM>(a, a.top);
 }
 
@@ -249,5 +251,236 @@ template <typename R, typename A, int DIM> __device__ void small_vcycle_body(con
     }
     team_vcycle<R, A, DIM, false>(a, top, wl);
 }
+
+// ---------------------------------------------------------------------------------------------------------------
+// (K-d3) the one-CTA kernel with the whole sub-hierarchy in SHARED MEMORY (round 2). k_small_vcycle above walks global
+// memory: every barrier phase is an L2 round trip (a store invalidates the line in L1) plus ~45 instructions per point
+// of index arithmetic and boundary selects -- 0.45-1.2 us per phase, 47 us per cycle at 2-D 64^2 fp64, which is the whole
+// of BASELINE config [0] and 16 % of config [4]. Here
+//  * every level's u, ping-pong partner and right-hand side live in shared memory for the whole launch, stored with a
+//    one-cell border of +0: a neighbour outside the grid reads 0 (cpu-raw.lua:36-39) without any select;
+//  * the level width is a template parameter (recursion over levels): index arithmetic is shifts and constant strides;
+//  * a thread keeps the right-hand side of its points in registers for all sweeps of a level visit;
+//  * a level is worked on by a TEAM of min(points, 1024) threads synchronised by a named barrier of exactly that many
+//    threads (a warp: __syncwarp), the rest of the CTA waits at the team barrier of the level above;
+//  * prolongation + add is an in-place phase of its own (u + prolong(V) rounded to storage, exactly addTo,
+//    cpu-raw.lua:83-85), then `smooth` plain sweeps.
+// Global memory is touched twice: all u (the persistent corrections Vs, cpu-raw.lua:164) and the top right-hand side
+// come in at the start; all u and the restricted right-hand sides Rs go back at the end.
+// Per-point arithmetic: mg_math.cuh as everywhere; summation order ((((xl+xr)+yl)+yr)+zl)+zr.
+template <int DIM, int LG> struct SmallGeom {
+    static constexpr int L = 1 << LG, P = L + 2;
+    static constexpr int N = DIM == 3 ? L * L * L : L * L;            // points
+    static constexpr int NP = DIM == 3 ? P * P * P : P * P;           // padded elements
+    static constexpr int NPP = (NP + 3) / 4 * 4;                      // one array, rounded up
+    static constexpr int TEAM = N >= 1024 ? 1024 : (N >= 32 ? N : 32);
+    static constexpr int PT = (N + TEAM - 1) / TEAM;                  // points per thread
+    static constexpr int NC = DIM == 3 ? N / 8 : N / 4;               // coarse cells below
+    static constexpr int CPT = (NC + TEAM - 1) / TEAM;
+};
+// element offset of level lg's three arrays (u, w, f): below it lie the levels 0 .. lg-1
+template <int DIM> __host__ __device__ constexpr int small_off(int lg)
+{
+    int o = 0;
+    for (int k = 0; k < lg; ++k) {
+        const int P = (1 << k) + 2, np = DIM == 3 ? P * P * P : P * P;
+        o += 3 * ((np + 3) / 4 * 4);
+    }
+    return o;
+}
+template <int DIM> static inline size_t small_smem_bytes(int top, size_t elem) { return (size_t)small_off<DIM>(top + 1) * elem; }
+static inline int small_team(int dim, int lg)
+{
+    const long n = 1L << (dim * lg);
+    return n >= 1024 ? 1024 : (n >= 32 ? (int)n : 32);
+}
+
+template <int TEAM, int ID> __device__ __forceinline__ void team_sync()
+{
+    if (TEAM <= 32) __syncwarp();
+    else asm volatile("bar.sync %0, %1;" ::"n"(ID), "n"(TEAM) : "memory");
+}
+// padded index of point idx = i + L (j + L k)
+template <int DIM, int LG> __device__ __forceinline__ int small_pidx(int idx)
+{
+    constexpr int L = 1 << LG, P = L + 2;
+    const int i = idx & (L - 1), j = (idx >> LG) & (L - 1);
+    int p = (i + 1) + P * (j + 1);
+    if (DIM == 3) p += P * P * ((idx >> (2 * LG)) + 1);
+    return p;
+}
+template <typename R, typename A, int DIM, int LG>
+__device__ __forceinline__ A small_stencil(const R *src, int p)
+{
+    constexpr int P = (1 << LG) + 2;
+    A S = Ar<A>::add(Ar<A>::add(Ar<A>::add((A)src[p - 1], (A)src[p + 1]), (A)src[p - P]), (A)src[p + P]);
+    if (DIM == 3) S = Ar<A>::add(Ar<A>::add(S, (A)src[p - P * P]), (A)src[p + P * P]);
+    return S;
+}
+
+template <typename R, typename A, int DIM, int LG> __device__ __noinline__ void small_level_smem(const SmallArgs<R, A> &a)
+{
+    typedef SmallGeom<DIM, LG> G;
+    extern __shared__ __align__(16) unsigned char small_smem_raw[];
+    R *const u = reinterpret_cast<R *>(small_smem_raw) + small_off<DIM>(LG), *const w = u + G::NPP, *const f = w + G::NPP;
+    const int tid = (int)threadIdx.x;
+    const Coef<A> c = a.coef[LG];
+    if constexpr (LG == 0) {
+        // L = 1: one smoother call (cpu-raw.lua:190-196); every neighbour is the +0 border
+        if (tid == 0) {
+            const int p = small_pidx<DIM, 0>(0);
+            const A S = small_stencil<R, A, DIM, 0>(u, p);
+            u[p] = (R)relax<A>(jacobi_point<DIM, A>(S, (A)f[p], c), (A)u[p], c);
+        }
+        __syncwarp();
+    } else {
+        constexpr int ID = 1 + LG;
+        const int smooth = a.smooth;
+        int pp[G::PT];
+        A fv[G::PT];
+#pragma unroll
+        for (int m = 0; m < G::PT; ++m) {
+            const int idx = tid + m * G::TEAM;
+            pp[m] = small_pidx<DIM, LG>(idx < G::N ? idx : 0);
+            fv[m] = (A)f[pp[m]];
+        }
+        const bool mine = G::N >= G::TEAM || tid < G::N;
+        R *src = u, *dst = w;
+        // all points of the thread together: their loads are issued before anything is stored (src and dst never
+        // alias, which the compiler cannot know) and the division guard of mg_math.cuh is one branch for the group
+        auto sweep = [&]() {
+            A num[G::PT], out[G::PT];
+#pragma unroll
+            for (int m = 0; m < G::PT; ++m) num[m] = jacobi_num<A>(small_stencil<R, A, DIM, LG>(src, pp[m]), fv[m], c);
+            div_adiag_group<DIM, A, G::PT>(num, out, c);
+            if (c.weighted) {
+#pragma unroll
+                for (int m = 0; m < G::PT; ++m) out[m] = relax<A>(out[m], (A)src[pp[m]], c);
+            }
+            if (mine) {
+#pragma unroll
+                for (int m = 0; m < G::PT; ++m) dst[pp[m]] = (R)out[m];
+            }
+            team_sync<G::TEAM, ID>();
+            R *t = src; src = dst; dst = t;
+        };
+        // ---- pre-smoothing, residual, restriction (cpu-raw.lua:198-218)
+        for (int s = 0; s < smooth; ++s) sweep();
+        {
+            typedef SmallGeom<DIM, LG - 1> GC;
+            R *const fc = reinterpret_cast<R *>(small_smem_raw) + small_off<DIM>(LG - 1) + 2 * GC::NPP;
+            constexpr int P = G::P;
+#pragma unroll
+            for (int m = 0; m < G::CPT; ++m) {
+                const int cidx = tid + m * G::TEAM;
+                if (cidx < G::NC) {
+                    constexpr int L2 = G::L / 2, LG2 = LG - 1;
+                    const int I = cidx & (L2 - 1), J = (cidx >> LG2) & (L2 - 1), K = DIM == 3 ? (cidx >> (2 * LG2)) : 0;
+                    const int p0 = (2 * I + 1) + P * (2 * J + 1) + (DIM == 3 ? P * P * (2 * K + 1) : 0);
+                    A sacc = (A)0;
+                    bool firstc = true;
+#pragma unroll
+                    for (int dk = 0; dk < (DIM == 3 ? 2 : 1); ++dk)
+#pragma unroll
+                        for (int dj = 0; dj < 2; ++dj)
+#pragma unroll
+                            for (int di = 0; di < 2; ++di) {
+                                const int p = p0 + di + P * dj + P * P * dk;
+                                const A S = small_stencil<R, A, DIM, LG>(src, p);
+                                const A rv = (A)(R)residual_point<A>(S, (A)f[p], (A)src[p], c);
+                                sacc = firstc ? rv : Ar<A>::add(sacc, rv);
+                                firstc = false;
+                            }
+                    fc[small_pidx<DIM, LG - 1>(cidx)] = (R)Ar<A>::mul(DIM == 3 ? (A).125 : (A).25, sacc);
+                }
+            }
+            team_sync<G::TEAM, ID>();
+            // ---- the level below, by its own (smaller or equal) team; everybody else waits for it here
+            if (tid < GC::TEAM) small_level_smem<R, A, DIM, LG - 1>(a);
+            team_sync<G::TEAM, ID>();
+            // ---- prolongation + add, in place (cpu-raw.lua:221-233): every thread corrects its own points
+            const R *const V = reinterpret_cast<R *>(small_smem_raw) + small_off<DIM>(LG - 1);
+#pragma unroll
+            for (int m = 0; m < G::PT; ++m) {
+                const int idx = tid + m * G::TEAM;
+                if (idx < G::N) {
+                    const int i = idx & (G::L - 1), j = (idx >> LG) & (G::L - 1), k = DIM == 3 ? (idx >> (2 * LG)) : 0;
+                    const int pc = ((i >> 1) + 1) + GC::P * ((j >> 1) + 1) + (DIM == 3 ? GC::P * GC::P * ((k >> 1) + 1) : 0);
+                    src[pp[m]] = (R)Ar<A>::add((A)src[pp[m]], (A)V[pc]);
+                }
+            }
+            team_sync<G::TEAM, ID>();
+        }
+        // ---- post-smoothing (cpu-raw.lua:234-236): 2 * smooth sweeps in total => the field is back in u
+        for (int s = 0; s < smooth; ++s) sweep();
+    }
+}
+
+template <typename R, typename A, int DIM, int LGMAX> struct SmallDispatch {
+    static __device__ __forceinline__ void run(const SmallArgs<R, A> &a)
+    {
+        if (a.top == LGMAX) small_level_smem<R, A, DIM, LGMAX>(a);
+        else if constexpr (LGMAX > 0) SmallDispatch<R, A, DIM, LGMAX - 1>::run(a);
+    }
+};
+// widest level (log2) the shared-memory kernel is instantiated for: 2-D 64^2, 3-D 16^3 (3 arrays per level with borders:
+// 143 KB / 163 KB for 8-byte reals)
+template <int DIM> struct SmallSmemMax { static constexpr int LG = DIM == 3 ? 4 : 6; };
+
+template <typename R, typename A, int DIM>
+__global__ void __launch_bounds__(1024, 1) k_small_vcycle_smem(const __grid_constant__ SmallArgs<R, A> a)
+{
+    pdl_enter();
+    extern __shared__ __align__(16) unsigned char small_smem_raw[];
+    R *const sm = reinterpret_cast<R *>(small_smem_raw);
+    const int tid = (int)threadIdx.x, nt = (int)blockDim.x, top = a.top;
+    const int total = small_off<DIM>(top + 1);
+    for (int e = tid; e < total; e += nt) sm[e] = (R)0;     // borders (and everything else) +0
+    __syncthreads();
+    // ---- in: every level's u (the corrections persist between cycles), the top level's right-hand side
+    // (the loads of a thread are all requested before the first of them is stored: one round trip, not one per level.
+    // Only the widest level the kernel is built for has more than one point per thread.)
+    {
+        constexpr int LGM = SmallSmemMax<DIM>::LG, PTM = SmallGeom<DIM, LGM>::PT;
+        R u1[LGM + 1], ux[PTM > 1 ? PTM - 1 : 1], fx[PTM];
+#pragma unroll
+        for (int lg = 0; lg <= LGM; ++lg) u1[lg] = (lg <= top && tid < (1 << (DIM * lg))) ? a.u[lg][tid] : (R)0;
+#pragma unroll
+        for (int m = 1; m < PTM; ++m) ux[m - 1] = top == LGM ? a.u[LGM][tid + m * nt] : (R)0;
+#pragma unroll
+        for (int m = 0; m < PTM; ++m) fx[m] = tid + m * nt < (1 << (DIM * top)) ? a.f[top][tid + m * nt] : (R)0;
+        auto put = [&](int lg, int idx, R uval, bool with_f, R fval) {
+            const int L = 1 << lg, P = L + 2;
+            const int np = ((DIM == 3 ? P * P * P : P * P) + 3) / 4 * 4;
+            const int i = idx & (L - 1), j = (idx >> lg) & (L - 1), k = DIM == 3 ? (idx >> (2 * lg)) : 0;
+            const int p = (i + 1) + P * (j + 1) + (DIM == 3 ? P * P * (k + 1) : 0);
+            R *const us = sm + small_off<DIM>(lg);
+            us[p] = uval;
+            if (with_f) us[2 * np + p] = fval;
+        };
+#pragma unroll
+        for (int lg = 0; lg <= LGM; ++lg)
+            if (lg <= top && tid < (1 << (DIM * lg))) put(lg, tid, u1[lg], lg == top, fx[0]);
+#pragma unroll
+        for (int m = 1; m < PTM; ++m)
+            if (top == LGM) put(LGM, tid + m * nt, ux[m - 1], true, fx[m]);
+    }
+    __syncthreads();
+    SmallDispatch<R, A, DIM, SmallSmemMax<DIM>::LG>::run(a);
+    __syncthreads();
+    // ---- out: every u, and the restricted right-hand sides below the top (Rs, as the global-memory kernel leaves them)
+    for (int lg = 0; lg <= top; ++lg) {
+        const int L = 1 << lg, P = L + 2, n = DIM == 3 ? L * L * L : L * L;
+        const int np = ((DIM == 3 ? P * P * P : P * P) + 3) / 4 * 4;
+        const R *const us = sm + small_off<DIM>(lg);
+        for (int idx = tid; idx < n; idx += nt) {
+            const int i = idx & (L - 1), j = (idx >> lg) & (L - 1), k = DIM == 3 ? (idx >> (2 * lg)) : 0;
+            const int p = (i + 1) + P * (j + 1) + (DIM == 3 ? P * P * (k + 1) : 0);
+            a.u[lg][idx] = us[p];
+            if (lg < top) const_cast<R *>(a.f[lg])[idx] = us[2 * np + p];
+        }
+    }
+}
+
 
 }  // namespace mg

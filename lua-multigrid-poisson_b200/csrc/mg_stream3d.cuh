@@ -76,6 +76,10 @@
                               // 0.47 -> 0.64 ms: an LDTM.x8 costs the SM ~16 cycles (64 B/clk) against 8 for the two LDS.128
                               // it replaces, and it does not overlap them; requesting a stage ahead did not help. Off.
 #endif
+#ifndef MG_SLAB_DEFER_HI
+#define MG_SLAB_DEFER_HI 1    // multi-GPU: the wait for the UPPER neighbour is deferred to the first request of a plane near the
+                              // top of the slab (0: both neighbours are awaited on entry)
+#endif
 #ifndef MG_STEADY_UNROLL
 #define MG_STEADY_UNROLL 2    // unroll factor of the steady-state step loop
 #endif
@@ -389,6 +393,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
     static_assert(MODE == S3_GUARDED || (kPackedF32 && std::is_same<A, float>::value && std::is_same<R, float>::value),
                   "the branch-free division is implemented for fp32 arithmetic");
     static_assert(MG_STREAM_SHFL || !PRO, "the register-path prolongation needs the shuffled x-neighbours");
+    pdl_enter();
     constexpr bool GUARDED = MODE != S3_FAST;
     typedef Stream3DCfg<R, S, RES, TX, TY> C;
     typedef typename Vec<R>::T VT;
@@ -427,13 +432,30 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         }
         skip = __syncthreads_or(redo) == 0;
     } else if (a.hs != nullptr) {
+        // The LOWER neighbour is needed at once (every column starts at the bottom of the slab: our lower ghost planes
+        // are read, its upper ghost planes written, within the first steps). The UPPER neighbour is only needed where a
+        // column reaches the top G planes of the slab -- its ghost planes are read, ours stored into it, nowhere else --
+        // so that wait is deferred to the first TMA request at or above plane nz_hi - G (hi_wait below): a pass no
+        // longer starts late because the rank above finished the previous one late. Thread 0 issues every TMA request
+        // and every other thread meets it at the step barrier before it can store anything of those planes.
         if (threadIdx.x == 0) {
             const unsigned long long n = s3_ld_acquire_sys(a.hs + HS_DONE);
             s3_wait_counter(a.hs_lo != nullptr ? a.hs + HS_FROM_LO : nullptr, n, a.hs);
-            s3_wait_counter(a.hs_hi != nullptr ? a.hs + HS_FROM_HI : nullptr, n, a.hs);
+            if (!MG_SLAB_DEFER_HI) s3_wait_counter(a.hs_hi != nullptr ? a.hs + HS_FROM_HI : nullptr, n, a.hs);
+            asm volatile("st.shared.u32 [%0], %1;" ::"r"(mb_u + NSLOT * 8 + 8), "r"(0u) : "memory");   // "upper neighbour awaited"
         }
         __syncthreads();
     }
+    // thread 0, before it requests source plane `plane` (local index): see above. HS_DONE does not change during a pass
+    // (the last CTA to finish bumps it), so it is read again here instead of living in a register.
+    auto hi_wait = [&](int plane) {
+        if (!MG_SLAB_DEFER_HI || MODE == S3_RERUN || a.hs_hi == nullptr || plane < a.nz_hi - a.ghost) return;
+        unsigned int waited;
+        asm volatile("ld.shared.u32 %0, [%1];" : "=r"(waited) : "r"(mb_u + NSLOT * 8 + 8) : "memory");
+        if (waited) return;
+        s3_wait_counter(a.hs + HS_FROM_HI, s3_ld_acquire_sys(a.hs + HS_DONE), a.hs);
+        asm volatile("st.shared.u32 [%0], %1;" ::"r"(mb_u + NSLOT * 8 + 8), "r"(1u) : "memory");
+    };
 
     // f planes in tensor memory: warp 0 allocates FT_COLS columns for the CTA; every thread then owns 2*VX*FTD columns
     // of its lane: lane 32 * (warp % 4) + laneid (implied by the warp), columns (warp / 4) * 64 onwards
@@ -503,6 +525,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
 #pragma unroll
         for (int k = 0; k < NSLOT - 1; ++k)
             if (k < nin) {      // nin >= 4: planes 0 and 1 always exist
+                hi_wait(zb + k);
                 mbar_expect_tx(mb_u + 8 * k, k == 1 && !FT ? 2 * C::PLANE_BYTES : C::PLANE_BYTES);
                 tma_load_3d(sbase + k * SB, &src_map, x0 - C::HX, y0 - C::HY, zb + k, mb_u + 8 * k);
             }
@@ -614,6 +637,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                 const int ks = su == 0 ? NSLOT - 1 : su - 1;  // (t + NSLOT - 1) % NSLOT
                 const int j = t + 1;                          // f plane stage 1 needs at step t + 2
                 int ksf = sf + 2; if (ksf >= NF) ksf -= NF;   // (t + 1) % NF  (sf = (t - 1) % NF)
+                hi_wait(zb + k);
                 // The slots being refilled were last READ through the generic proxy before the barrier that ended
                 // step t-1 (the values are in registers); nothing writes them through the generic proxy.
                 mbar_expect_tx(mb_u + 8 * ks, FT ? C::PLANE_BYTES : 2 * C::PLANE_BYTES);

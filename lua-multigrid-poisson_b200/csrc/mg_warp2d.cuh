@@ -75,6 +75,7 @@ __global__ void __launch_bounds__(128, MG_WARP2D_MIN_CTAS)
 k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f, const R *__restrict__ Vp,
          R *__restrict__ Rout, int L, int TY, int nstrips, int nitems, Coef<A> cf)
 {
+    pdl_enter();
     typedef Warp2DCfg<S, RES> C;
     constexpr int NST = C::NST, H = C::H;
     constexpr bool PACKED = MG_PACKED_F32 != 0 && std::is_same<A, float>::value && std::is_same<R, float>::value;
