@@ -632,6 +632,59 @@ def run_ours(args):
         except Exception as e:
             ttt = {"unavailable": repr(e)[:200]}
 
+    # ---- where a rank's cycle goes on N GPUs: the kernels' own timeline of the distributed passes (mg_slab_trace)
+    timeline = None
+    if world > 1:
+        try:
+            s.init_cells(); s.zero_corrections()
+            s.set_option("slab_trace", 1)
+            for _ in range(3):
+                lib.mg_vcycle_async(h)         # ghost refresh, graph capture
+            barrier()
+            s.set_option("slab_trace", 1)      # reset the records (the graph is captured again: the trace pointer is an argument)
+            lib.mg_vcycle_async(h)
+            barrier()
+            s.set_option("slab_trace", 1)
+            ncyc = 6
+            for _ in range(ncyc):
+                lib.mg_vcycle_async(h)
+            barrier()
+            tr = s.slab_trace().astype(np.int64)
+            s.set_option("slab_trace", 0)
+            npass = len(tr) // ncyc
+            mine = None
+            if npass > 0 and len(tr) == npass * ncyc:
+                t = tr.reshape(ncyc, npass, 4)[1:]                       # drop the first cycle
+                flat = tr.reshape(-1, 4)
+                gap = np.zeros(len(flat)); gap[1:] = flat[1:, 0] - flat[:-1, 3]
+                gap = gap.reshape(ncyc, npass)[1:]
+                mine = {"lo_wait_us": ((t[:, :, 1] - t[:, :, 0]).mean(0) / 1e3).tolist(),
+                        "hi_wait_us": (t[:, :, 2].mean(0) / 1e3).tolist(),
+                        "pass_us": ((t[:, :, 3] - t[:, :, 0]).mean(0) / 1e3).tolist(),
+                        "gap_before_us": (gap.mean(0) / 1e3).tolist(),
+                        "cycle_us": float((flat[npass:, 0].reshape(ncyc - 1, npass)[-1, 0] - flat[npass, 0]) / max(ncyc - 2, 1) / 1e3)}
+            allr = [None] * world
+            dist.all_gather_object(allr, mine)
+            if rank == 0 and all(a is not None for a in allr):
+                def agg(key, f):
+                    return [round(float(f([a[key][j] for a in allr])), 1) for j in range(len(allr[0][key]))]
+                timeline = {"passes_per_cycle": len(allr[0]["pass_us"]),
+                            "order": "distributed levels top-down (pre-smoothing passes), then bottom-up (post-smoothing passes)",
+                            "pass_us_max_over_ranks": agg("pass_us", max), "pass_us_mean": agg("pass_us", np.mean),
+                            "lo_wait_us_mean": agg("lo_wait_us", np.mean), "lo_wait_us_max": agg("lo_wait_us", max),
+                            "hi_wait_us_mean": agg("hi_wait_us", np.mean), "hi_wait_us_max": agg("hi_wait_us", max),
+                            "gap_before_us_mean": agg("gap_before_us", np.mean),
+                            "sum_pass_us_mean": round(float(np.mean([sum(a["pass_us"]) for a in allr])), 1),
+                            "sum_gap_us_mean": round(float(np.mean([sum(a["gap_before_us"]) for a in allr])), 1),
+                            "sum_wait_us_mean": round(float(np.mean([sum(a["lo_wait_us"]) + sum(a["hi_wait_us"]) for a in allr])), 1),
+                            "cycle_us_mean": round(float(np.mean([a["cycle_us"] for a in allr])), 1),
+                            "note": "globaltimer stamps written by the smoother kernels themselves (CTA 0 on entry / after the wait for "
+                                    "the lower neighbour, its deferred wait for the upper neighbour, the last CTA at the end); gap_before "
+                                    "= entry minus the previous pass's end: launch gaps, and for the first post-smoothing pass of the "
+                                    "last distributed level the epoch fence + the whole replicated coarse sub-cycle"}
+        except Exception as e:
+            timeline = {"unavailable": repr(e)[:300]}
+
     mgcg = None
     if rank == 0 and world == 1 and (args.dim, args.size, args.real) == (2, 2048, "double"):
         try:
@@ -654,6 +707,7 @@ def run_ours(args):
         if world > 1:
             line["parity"] = parity
             line["nvlink"] = nvl
+            line["slab_timeline"] = timeline
         print(json.dumps(line))
     s.close()
     if dist is not None:

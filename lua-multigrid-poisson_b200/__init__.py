@@ -130,6 +130,7 @@ def lib():
         "mg_set_global_option": (i, [C.c_char_p, i]),
         "mg_set_omega": (i, [vp, d]),
         "mg_slab_traffic": (i, [vp, C.POINTER(u64), C.POINTER(u64)]),
+        "mg_slab_trace": (i, [vp, C.POINTER(u64), sz, C.POINTER(sz)]),
         "mg_slab_ipc_export": (i, [vp, vp, sz]),
         "mg_slab_ipc_attach": (i, [vp, vp, sz]),
         "mg_slab_info": (i, [vp, pi, pi, pi, pi, C.POINTER(u64), C.POINTER(u64)]),
@@ -311,6 +312,14 @@ class MultigridCUDA:
         a, b = C.c_uint64(), C.c_uint64()
         self._ck(lib().mg_slab_traffic(self._h, C.byref(a), C.byref(b)))
         return dict(peer_store_bytes=a.value, exchange_bytes=b.value)
+
+    def slab_trace(self, cap=4096):
+        """Timeline of this rank's distributed smoother passes since set_option("slab_trace", 1): an (n, 4) uint64 array
+        {entry, after the lower-neighbour wait, ns waited for the upper neighbour, end} in this GPU's nanoseconds."""
+        buf = (C.c_uint64 * (4 * cap))()
+        n = C.c_size_t()
+        self._ck(lib().mg_slab_trace(self._h, buf, cap, C.byref(n)))
+        return np.ctypeslib.as_array(buf)[: 4 * n.value].reshape(-1, 4).copy()
 
     def info(self):
         v = [C.c_int() for _ in range(5)]

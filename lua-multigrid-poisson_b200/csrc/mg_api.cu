@@ -151,6 +151,12 @@ int mg_set_option(mg_ctx *ctx, const char *name, int value)
         }
     }
     else if (n == "lockstep") ctx->lockstep_opt = value;
+    else if (n == "slab_trace") {   // timeline of the slab passes (mg_slab_trace): 1 = record (and reset), 0 = off
+        const size_t bytes = sizeof(unsigned long long) * (8 + 4 * (size_t)S3_TRACE_CAP);
+        if (value && !ctx->slab_trace) MG_CK(ctx, cudaMalloc(&ctx->slab_trace, bytes));
+        if (value) MG_CK(ctx, cudaMemset(ctx->slab_trace, 0, bytes));
+        if (!value && ctx->slab_trace) { MG_CK(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->slab_trace); ctx->slab_trace = nullptr; }
+    }
     else if (n == "small_smem") { for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) { m->small_smem_opt = value; m->drop_graph(); } }
     else if (n == "pdl") { for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) { m->pdl_opt = value != 0; m->drop_graph(); } }
     else if (n == "colparts") { for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) m->colparts_opt = value; }
@@ -727,6 +733,23 @@ int mg_slab_traffic(mg_ctx *ctx, uint64_t *peer_store_bytes, uint64_t *exchange_
     for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) b += m->nvl_bytes;
     if (peer_store_bytes) *peer_store_bytes = b;
     if (exchange_bytes) *exchange_bytes = ctx->group ? ctx->group->exchanged_bytes : 0;
+    return MG_OK;
+}
+
+// Timeline of this rank's slab passes since option "slab_trace" = 1: up to cap records of 4 words each
+// {ns on entry, ns after the wait for the lower neighbour, ns CTA 0 waited for the upper neighbour, ns when the last CTA
+// finished}, device globaltimer of THIS GPU (differences are meaningful, absolute values are not comparable across GPUs).
+int mg_slab_trace(mg_ctx *ctx, uint64_t *records, size_t cap, size_t *n)
+{
+    CTX_OR_FAIL(ctx);
+    if (!ctx->slab_trace) return ctx->fail(MG_ESTATE, "mg_slab_trace: set option slab_trace = 1 first");
+    MG_CK(ctx, cudaStreamSynchronize(ctx->stream));
+    unsigned long long cnt = 0;
+    MG_CK(ctx, cudaMemcpy(&cnt, ctx->slab_trace, sizeof(cnt), cudaMemcpyDeviceToHost));
+    size_t m = cnt < S3_TRACE_CAP ? (size_t)cnt : (size_t)S3_TRACE_CAP;
+    if (m > cap) m = cap;
+    if (records && m) MG_CK(ctx, cudaMemcpy(records, ctx->slab_trace + 8, m * 4 * sizeof(uint64_t), cudaMemcpyDeviceToHost));
+    if (n) *n = m;
     return MG_OK;
 }
 

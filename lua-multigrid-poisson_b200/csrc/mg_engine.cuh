@@ -151,6 +151,7 @@ struct mg_ctx {
     char *peer_lo = nullptr, *peer_hi = nullptr;
     char *peer[mg::S3_MAX_RANKS] = {};   // every rank's arena as seen from this rank (peer[rank] = arena); null = not mapped
     bool peer_ipc = false, p2p = false, slab_graph_opt = true;
+    unsigned long long *slab_trace = nullptr;   // timeline of the slab passes (option "slab_trace"; Stream3DArgs::trace)
     size_t Ntop = 0;                    // elements allocated for a top-level field (incl. ghosts)
 
     int planes(int lv) const { return dist[lv] ? nzl[lv] + 2 * G : (dim == 3 ? (1 << lv) : 1); }
@@ -504,7 +505,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         dim3 grid((unsigned)ncta, 1, 1);
         Stream3DArgs<R> a{dst, Vp, Rout, L, c->stream_flags, nz_lo, nz_hi, zdom0, zdom0 + L, rz_off, vz_off,
                           nullptr, nullptr, nullptr, nullptr, c->G, nullptr, nullptr, nullptr, ncol, zcol, rem_cta0, rem_tile0, rem_z0,
-                          (unsigned int *)((char *)c->arena + ARENA_REDO_OFF), f};
+                          (unsigned int *)((char *)c->arena + ARENA_REDO_OFF), f, {}, 0, nullptr};
         if (c->dist[lv] && c->p2p) {  // fused halo exchange: same offsets inside the neighbours' arenas
             const size_t doff = c->arena_off(dst);
             if (c->peer_lo) a.peer_lo = (R *)(c->peer_lo + doff);
@@ -531,6 +532,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
                 a.hs = (unsigned long long *)c->arena;
                 a.hs_lo = (unsigned long long *)c->peer_lo;
                 a.hs_hi = (unsigned long long *)c->peer_hi;
+                a.trace = c->slab_trace;
             }
         }
         c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : (RES ? MG_K_SWEEP_RESTRICT : MG_K_SWEEP), L, S);
@@ -1366,6 +1368,8 @@ inline void mg_ctx::release()
     if (d_partial) cudaFree(d_partial);
     if (cg_tmp) cudaFree(cg_tmp);
     cg_tmp = nullptr;
+    if (slab_trace) cudaFree(slab_trace);
+    slab_trace = nullptr;
     if (h_scalar) cudaFreeHost(h_scalar);
     if (own_stream) cudaStreamDestroy(own_stream);
     if (cap_stream) cudaStreamDestroy(cap_stream);

@@ -77,7 +77,7 @@
                               // it replaces, and it does not overlap them; requesting a stage ahead did not help. Off.
 #endif
 #ifndef MG_SLAB_DEFER_HI
-#define MG_SLAB_DEFER_HI 1    // multi-GPU: the wait for the UPPER neighbour is deferred to the first request of a plane near the
+#define MG_SLAB_DEFER_HI 0    // multi-GPU: the wait for the UPPER neighbour is deferred to the first request of a plane near the
                               // top of the slab (0: both neighbours are awaited on entry)
 #endif
 #ifndef MG_STEADY_UNROLL
@@ -371,7 +371,12 @@ template <typename R> struct Stream3DArgs {
     // copy of the coarse cube -- the all-gather of the first replicated level, done by the producing threads.
     R *rall[S3_MAX_RANKS];
     int rall_n;
+    // Timeline of the slab passes (option "slab_trace", measurement only; null = off): word 0 counts the passes recorded,
+    // record i = words 8 + 4 i .. : {globaltimer on entry, after the wait for the lower neighbour, ns CTA 0 spent waiting
+    // for the upper neighbour, globaltimer when the last CTA finished}. Written by CTA 0 / the last CTA only.
+    unsigned long long *trace;
 };
+constexpr unsigned int S3_TRACE_CAP = 4096;   // records in the timeline buffer (it wraps)
 
 // MODE: how the division guard of mg_math.cuh (a tiny but non-zero numerator needs IEEE division) is handled.
 //   S3_GUARDED  every stage tests its group of numerators and branches to IEEE division (all arithmetic types);
@@ -439,9 +444,13 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         // longer starts late because the rank above finished the previous one late. Thread 0 issues every TMA request
         // and every other thread meets it at the step barrier before it can store anything of those planes.
         if (threadIdx.x == 0) {
+            const bool tr = a.trace != nullptr && blockIdx.x == 0;
+            unsigned long long *rec = nullptr;
+            if (tr) { rec = a.trace + 8 + 4 * (a.trace[0] & (S3_TRACE_CAP - 1)); rec[0] = s3_globaltimer(); rec[2] = 0ull; }
             const unsigned long long n = s3_ld_acquire_sys(a.hs + HS_DONE);
             s3_wait_counter(a.hs_lo != nullptr ? a.hs + HS_FROM_LO : nullptr, n, a.hs);
             if (!MG_SLAB_DEFER_HI) s3_wait_counter(a.hs_hi != nullptr ? a.hs + HS_FROM_HI : nullptr, n, a.hs);
+            if (tr) rec[1] = s3_globaltimer();
             asm volatile("st.shared.u32 [%0], %1;" ::"r"(mb_u + NSLOT * 8 + 8), "r"(0u) : "memory");   // "upper neighbour awaited"
         }
         __syncthreads();
@@ -453,7 +462,10 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
         unsigned int waited;
         asm volatile("ld.shared.u32 %0, [%1];" : "=r"(waited) : "r"(mb_u + NSLOT * 8 + 8) : "memory");
         if (waited) return;
+        const bool tr = a.trace != nullptr && blockIdx.x == 0;
+        const unsigned long long t0 = tr ? s3_globaltimer() : 0ull;
         s3_wait_counter(a.hs + HS_FROM_HI, s3_ld_acquire_sys(a.hs + HS_DONE), a.hs);
+        if (tr) a.trace[8 + 4 * (a.trace[0] & (S3_TRACE_CAP - 1)) + 2] = s3_globaltimer() - t0;
         asm volatile("st.shared.u32 [%0], %1;" ::"r"(mb_u + NSLOT * 8 + 8), "r"(1u) : "memory");
     };
 
@@ -637,7 +649,7 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
                 const int ks = su == 0 ? NSLOT - 1 : su - 1;  // (t + NSLOT - 1) % NSLOT
                 const int j = t + 1;                          // f plane stage 1 needs at step t + 2
                 int ksf = sf + 2; if (ksf >= NF) ksf -= NF;   // (t + 1) % NF  (sf = (t - 1) % NF)
-                hi_wait(zb + k);
+                if constexpr (!ST) hi_wait(zb + k);   // (the steady-state loop is split around that plane instead, see below)
                 // The slots being refilled were last READ through the generic proxy before the barrier that ended
                 // step t-1 (the values are in registers); nothing writes them through the generic proxy.
                 mbar_expect_tx(mb_u + 8 * ks, FT ? C::PLANE_BYTES : 2 * C::PLANE_BYTES);
@@ -998,12 +1010,22 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
 #pragma unroll 1
     for (int phase = 0; phase < 3; ++phase) {
         if (phase == 1) {
-            if (cta_inner && !(a.flags & 2)) {
+            // Multi-GPU: the step that requests the first source plane at or above nz_hi - G (plane zb + t + NSLOT - 1) must
+            // come after the wait for the upper neighbour (hi_wait). The steady-state body itself stays free of it (a spin
+            // loop inside the body cost 19 % of a pass, measured): the loop runs in two parts around that step.
+            int t_mid = t_hi + 1;
+            if (MG_SLAB_DEFER_HI && a.hs_hi != nullptr) t_mid = max(t_lo, min(t_hi + 1, a.nz_hi - a.ghost - zb - (NSLOT - 1)));
+#pragma unroll 1
+            for (int part = 0; part < 2; ++part) {
+                const int ta = part == 0 ? t_lo : t_mid, tb = part == 0 ? t_mid - 1 : t_hi;
+                if (part == 1 && tid == 0 && ta <= tb) hi_wait(a.nz_hi);
+                if (cta_inner && !(a.flags & 2)) {
 #pragma unroll kSteadyUnroll
-                for (int t = t_lo; t <= t_hi; ++t) step(std::true_type{}, std::false_type{}, t);
-            } else {
+                    for (int t = ta; t <= tb; ++t) step(std::true_type{}, std::false_type{}, t);
+                } else {
 #pragma unroll kSteadyUnroll
-                for (int t = t_lo; t <= t_hi; ++t) step(std::true_type{}, std::true_type{}, t);
+                    for (int t = ta; t <= tb; ++t) step(std::true_type{}, std::true_type{}, t);
+                }
             }
         } else {
             const int ta = phase == 0 ? 0 : t_hi + 1, tb = phase == 0 ? min(t_lo, T) : T;
@@ -1061,6 +1083,11 @@ k_stream3d(const __grid_constant__ CUtensorMap src_map, const __grid_constant__ 
             const unsigned int done = atomicAdd(reinterpret_cast<unsigned int *>(a.hs + HS_CTAS), 1u);
             if (done == gridDim.x - 1) {
                 *reinterpret_cast<volatile unsigned int *>(a.hs + HS_CTAS) = 0u;
+                if (a.trace != nullptr) {
+                    const unsigned long long i = a.trace[0];
+                    a.trace[8 + 4 * (i & (S3_TRACE_CAP - 1)) + 3] = s3_globaltimer();
+                    a.trace[0] = i + 1;
+                }
                 const unsigned long long n = s3_ld_acquire_sys(a.hs + HS_DONE) + 1;
                 s3_st_release_sys(a.hs + HS_DONE, n);
                 if (a.hs_lo != nullptr) s3_st_release_sys(a.hs_lo + HS_FROM_HI, n);   // we are its upper neighbour

@@ -188,6 +188,10 @@ int mg_slab_info(mg_ctx *ctx, int *rank, int *nranks, int *own_planes, int *ghos
 /* bytes stored straight into other GPUs' memory by this handle's kernels (fused halo exchange + fused all-gather),
  * and bytes moved by explicit exchanges (NCCL send/recv or peer copies), since creation */
 int mg_slab_traffic(mg_ctx *ctx, uint64_t *peer_store_bytes, uint64_t *exchange_bytes);
+/* measurement: after mg_set_option(ctx, "slab_trace", 1) every distributed smoother pass of this rank records 4 words
+ * {ns on entry, ns after the wait for the lower neighbour, ns its first CTA waited for the upper neighbour, ns when its
+ * last CTA finished} (this GPU's globaltimer). Copies up to cap records (the first ones since the option was set). */
+int mg_slab_trace(mg_ctx *ctx, uint64_t *records, size_t cap, size_t *n);
 ]]
 
 local lib = ffi.load(os.getenv'MGPOISSON_LIB' or 'mgpoisson')

@@ -218,6 +218,11 @@ int main(int argc, char **argv)
         printf(", \"s3_ms\": %.4f", t);
         if (check) { float *r = ref_sweeps(3, false); unsigned long long d = diff(w, r, n, d_cnt); bad += d; printf(", \"s3_bad\": %llu", d); }
     }
+    {   // alternative post-smoothing plan [PRO+3][4] (not part of level_visit_ms)
+        float t = run_pass<3, true, false>(L, w, u, f, V, nullptr, reps, &zs);
+        printf(", \"pro3_ms\": %.4f", t);
+        if (check) { float *r = ref_sweeps(3, true); unsigned long long d = diff(w, r, n, d_cnt); bad += d; printf(", \"pro3_bad\": %llu", d); }
+    }
     printf(", \"level_visit_ms\": %.4f, \"bad\": %llu}\n", total, bad);
     return bad ? 1 : 0;
 }
