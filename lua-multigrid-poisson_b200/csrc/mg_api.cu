@@ -151,6 +151,7 @@ int mg_set_option(mg_ctx *ctx, const char *name, int value)
         }
     }
     else if (n == "lockstep") ctx->lockstep_opt = value;
+    else if (n == "block_max_L") { for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) { m->block_max_L = value; m->drop_graph(); } }
     else if (n == "slab_trace") {   // timeline of the slab passes (mg_slab_trace): 1 = record (and reset), 0 = off
         const size_t bytes = sizeof(unsigned long long) * (8 + 4 * (size_t)S3_TRACE_CAP);
         if (value && !ctx->slab_trace) MG_CK(ctx, cudaMalloc(&ctx->slab_trace, bytes));
@@ -158,7 +159,7 @@ int mg_set_option(mg_ctx *ctx, const char *name, int value)
         if (!value && ctx->slab_trace) { MG_CK(ctx, cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->slab_trace); ctx->slab_trace = nullptr; }
     }
     else if (n == "small_smem") { for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) { m->small_smem_opt = value; m->drop_graph(); } }
-    else if (n == "pdl") { for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) { m->pdl_opt = value != 0; m->drop_graph(); } }
+    else if (n == "pdl") { for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) { m->pdl_opt = value; m->drop_graph(); } }
     else if (n == "colparts") { for (mg_ctx *m : (ctx->group ? ctx->group->m : std::vector<mg_ctx *>{ctx})) m->colparts_opt = value; }
     else if (n == "fastdiv") ctx->fastdiv_opt = value;
     else if (n == "fast_min_L") ctx->fast_min_L = value;

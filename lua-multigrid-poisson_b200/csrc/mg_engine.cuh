@@ -14,6 +14,7 @@
 #include <vector>
 
 #include "../../include/mgpoisson.h"
+#include "mg_block3d.cuh"
 #include "mg_fused_simple.cuh"
 #include "mg_krylov.cuh"
 #include "mg_math.cuh"
@@ -82,6 +83,9 @@ struct mg_ctx {
     int ty_override = 0;     // 2-D: rows per warp work item (0 = cost model)
     int stream_min_L = 128;  // smallest level width handled by the streaming (TMA) smoother
     int num_sms = 148;       // SM count of the device (queried at init)
+    int block_max_L = 0;     // 3-D: widest level handled by the block-temporal kernel (mg_block3d.cuh); 0 = off, the default.
+                             // MEASURED (round 2, 512^3 fp32, V-cycles/s inside the CUDA graph): off 405.1, 32^3 only 402.5,
+                             // 32^3 + 64^3 398.8 -- 20 fewer launches per cycle do not pay for the 2-4.5 x redundant halo work.
     int small_smem_opt = 1;  // levels <= small_L by the shared-memory one-CTA kernel (0: the global-memory walker)
     int pdl_opt = 0;         // kernels of a V-cycle launched with programmatic stream serialization (mg_math.cuh, pdl_enter).
                              // MEASURED (round 2, same box): 512^3 fp32 397.1 -> 393.3 V-cycles/s, 2-D 4096^2 fp32 and 2048^2 fp64
@@ -254,15 +258,20 @@ static inline dim3 block_for(int L)
 // Launch of a V-cycle kernel (every one of them starts with pdl_enter()): with the "pdl" option the launch carries
 // cudaLaunchAttributeProgrammaticStreamSerialization, which also survives stream capture as a programmatic graph edge.
 template <typename... KArgs, typename... Args>
-static inline cudaError_t launch_k(mg_ctx *c, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args)
+static inline cudaError_t launch_k2(mg_ctx *c, bool pdl, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args)
 {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = c->stream;
     cudaLaunchAttribute at[1];
     at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     at[0].val.programmaticStreamSerializationAllowed = 1;
-    cfg.attrs = at; cfg.numAttrs = c->pdl_opt ? 1 : 0;
+    cfg.attrs = at; cfg.numAttrs = pdl ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
+template <typename... KArgs, typename... Args>
+static inline cudaError_t launch_k(mg_ctx *c, void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, Args &&...args)
+{
+    return launch_k2(c, c->pdl_opt == 1, kern, grid, block, smem, std::forward<Args>(args)...);
 }
 
 template <typename R, typename A, int DIM> struct EngineT : Engine {
@@ -539,7 +548,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         MG_CK(c, launch_k(c, kern, grid, dim3(C::NTHREADS), C::SMEM_BYTES, *map, *fmap, a, cf));
         if (kern2) {
             MG_LAUNCH_CHECK(c);
-            MG_CK(c, launch_k(c, kern2, grid, dim3(C::NTHREADS), C::SMEM_BYTES, *map, *fmap, a, cf));
+            MG_CK(c, launch_k2(c, c->pdl_opt != 0, kern2, grid, dim3(C::NTHREADS), C::SMEM_BYTES, *map, *fmap, a, cf));   // "pdl" = 2: this edge only
         }
         c->prof_end();
         MG_LAUNCH_CHECK(c);
@@ -853,6 +862,33 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         return MG_OK;
     }
 
+    // ---- block-temporal passes of the mid levels (mg_block3d.cuh), 3-D only
+    template <int S, bool PRO, int BX, int BY, int BZ>
+    int launch_block3d(mg_ctx *c, int L, R *dst, const R *src, const R *f, const R *Vp, const Coef<A> &cf)
+    {
+        typedef Block3DCfg<S, BX, BY, BZ> C;
+        auto kern = k_block3d<R, A, S, PRO, BX, BY, BZ>;
+        constexpr int smem = C::template smem_bytes<R>();
+        MG_CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        const unsigned nblk = (unsigned)((L / BX) * (L / BY) * (L / BZ));
+        c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : MG_K_SWEEP, L, S);
+        MG_CK(c, launch_k(c, kern, dim3(nblk), dim3(C::NTHREADS), (size_t)smem, dst, src, f, Vp, L, cf));
+        c->prof_end();
+        MG_LAUNCH_CHECK(c);
+        return MG_OK;
+    }
+    int block3d_pass(mg_ctx *c, int L, int S, bool pro, R *dst, const R *src, const R *f, const R *Vp, const Coef<A> &cf)
+    {
+        if constexpr (DIM == 3) {
+#define MG_B3D(S_, P_) \
+    return L <= 32 ? launch_block3d<S_, P_, 8, 8, 8>(c, L, dst, src, f, Vp, cf) : launch_block3d<S_, P_, 16, 16, 8>(c, L, dst, src, f, Vp, cf)
+            if (pro) { switch (S) { case 1: MG_B3D(1, true); case 2: MG_B3D(2, true); case 3: MG_B3D(3, true); case 4: MG_B3D(4, true); } }
+            else { switch (S) { case 1: MG_B3D(1, false); case 2: MG_B3D(2, false); case 3: MG_B3D(3, false); case 4: MG_B3D(4, false); } }
+#undef MG_B3D
+        }
+        return c->fail(MG_EINVAL, "block3d_pass: unsupported combination");
+    }
+
     int sweeps(mg_ctx *c, int lv, R *&cur, R *&oth, const R *f, double h, int n, const R *Vp, R *Rout)
     {
         const int L = 1 << lv;
@@ -862,12 +898,26 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
             if (ref_omega && c->tb2 >= 1 && L >= c->warp2d_min_L && n >= 1 && !(Vp && Rout && n <= c->tb2))
                 return sweeps_warp2d(c, L, cur, oth, f, cf, n, Vp, Rout);
         }
+        // 3-D mid levels that are not cut into slabs: up to 4 sweeps per launch in shared memory (mg_block3d.cuh)
+        const bool use_block = DIM == 3 && ref_omega && n >= 1 && L >= 32 && L <= c->block_max_L && !c->dist[lv];
         if constexpr (DIM == 3) {
-            if (ref_omega && c->tb >= 1 && L >= c->stream_min_L && n >= 1 && !(Vp && Rout && n <= c->tb))
+            if (!use_block && ref_omega && c->tb >= 1 && L >= c->stream_min_L && n >= 1 && !(Vp && Rout && n <= c->tb))
                 return sweeps_stream3d(c, lv, cur, oth, f, cf, n, Vp, Rout);
         }
         dim3 b = block_for(L), g = grid_for(DIM, L, b);
-        for (int s = 0; s < n; ++s) {
+        bool blocked = false;
+        if constexpr (DIM == 3) {
+            if (use_block) {
+                const std::vector<int> plan = plan_passes(n, 4, false);
+                for (size_t i = 0; i < plan.size(); ++i) {
+                    int rc = block3d_pass(c, L, plan[i], i == 0 && Vp, oth, cur, f, Vp, cf);
+                    if (rc) return rc;
+                    R *t = cur; cur = oth; oth = t;
+                }
+                blocked = true;
+            }
+        }
+        for (int s = 0; s < n && !blocked; ++s) {
             c->prof_begin(s == 0 && Vp ? MG_K_SWEEP_PROLONG : MG_K_SWEEP, L, 1);
             if (s == 0 && Vp)
                 MG_CK(c, launch_k(c, k_sweep_pp<R, A, DIM, true>, g, b, 0, oth, (const R *)cur, f, Vp, L, cf));
@@ -1004,7 +1054,7 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         at[0].val.clusterDim.x = (unsigned)c->cluster_ctas; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
         at[1].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at; cfg.numAttrs = c->pdl_opt ? 2 : 1;
+        cfg.attrs = at; cfg.numAttrs = c->pdl_opt == 1 ? 2 : 1;
         c->prof_begin(MG_K_SMALL, 1 << lv, 2 * c->smooth);
         MG_CK(c, cudaLaunchKernelEx(&cfg, kern, ca));
         c->prof_end();
@@ -1269,7 +1319,8 @@ inline int mg_ctx::init(int dim_, int size_, int real_kind_, int smooth_, int de
             if (L >= 64 && L / nranks >= min_planes) { dist[lv] = true; nzl[lv] = L / nranks; }
         }
         if (!dist[nlevels - 1]) return fail(MG_EINVAL, "grid too small to be cut into slabs (need size >= 64 and size/nranks >= slab_min_planes, 32 by default)");
-        stream_min_L = 64;
+        // (replicated levels run the single-GPU path with the single-GPU thresholds: 64^3 through the one-sweep launches
+        // is 36 us per cycle cheaper than through the streaming kernel, measured at N = 1; distributed levels always stream)
         tb = 4;
     }
     N = (size_t)size * size * (dim == 3 ? (size_t)size : 1);

@@ -88,3 +88,34 @@ def test_programmatic_dependent_launch_does_not_change_a_single_bit(mgp, dim, si
         assert errs == ref[0], key
         for k, v in ref[1].items():
             assert_bits_equal(lv[k], v, f"{k} pdl,graph={key}")
+
+
+@pytest.mark.parametrize("real", KINDS)
+def test_block_temporal_mid_level_kernel_does_not_change_a_single_bit(mgp, real):
+    """mg_block3d.cuh: up to 4 sweeps per launch on the 32^3 / 64^3 (optionally 128^3) levels, against one sweep per
+    launch (block_max_L = 0) -- every field of the hierarchy, three cycles."""
+    got = {}
+    for bmax in (0, 32, 64, 128):
+        s = mgp.MultigridCUDA(128, real, dim=3, out=False)
+        s.set_option("block_max_L", bmax)
+        errs = [s.step() for _ in range(3)]
+        got[bmax] = (errs, _levels(s, 128))
+        s.close()
+    for bmax in (32, 64, 128):
+        assert got[bmax][0] == got[0][0], bmax
+        for k, v in got[0][1].items():
+            assert_bits_equal(got[bmax][1][k], v, f"{k} block_max_L={bmax} {real}")
+
+
+@pytest.mark.parametrize("smooth", [1, 2, 3, 4, 5, 8])
+def test_block_temporal_kernel_sweep_counts(mgp, smooth):
+    """every split of the sweep count into passes of <= 4, with and without the fused prolongation"""
+    got = {}
+    for bmax in (0, 64):
+        s = mgp.MultigridCUDA(64, "float", dim=3, smooth=smooth, out=False)
+        s.set_option("block_max_L", bmax)
+        s.vcycle(); s.vcycle()
+        got[bmax] = _levels(s, 64)
+        s.close()
+    for k, v in got[0].items():
+        assert_bits_equal(got[64][k], v, f"{k} smooth={smooth}")

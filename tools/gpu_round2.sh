@@ -22,7 +22,7 @@ if [ -n "$NCU" ]; then
 B="python bench.py --steps 3 --warmup 3 --no-cpu"
 $B > gpurun_out/${TAG}_plain.log 2>&1 && \
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/${TAG}_launches_3d_512_float.csv $B > gpurun_out/${TAG}_ncu1.log 2>&1; echo "ncu launches rc=$?"
-ncu --metrics $M --clock-control none -k regex:k_stream3d -s 0 -c 20 --csv --log-file gpurun_out/${TAG}_metrics_3d_512_float.csv $B > gpurun_out/${TAG}_ncu2.log 2>&1; echo "ncu metrics 3d rc=$?"
+ncu --metrics $M --clock-control none -k regex:k_stream3d -s 0 -c 24 --csv --log-file gpurun_out/${TAG}_metrics_3d_512_float.csv $B > gpurun_out/${TAG}_ncu2.log 2>&1; echo "ncu metrics 3d rc=$?"
 ncu --set full --clock-control none --import-source on -k regex:"k_stream3d<float, float, \(int\)4, \(bool\)1" -s 0 -c 1 -f -o gpurun_out/prof_${TAG}_3d_512_float_top $B > gpurun_out/${TAG}_ncu3.log 2>&1; echo "ncu full top rc=$?"
 B="python bench.py --config c2 --steps 3 --warmup 3 --no-cpu"
 $B > gpurun_out/${TAG}_plain2.log 2>&1 && \
