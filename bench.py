@@ -441,8 +441,8 @@ def run_ours(args):
     # run a second time by the guarded kernel (mg_stream3d.cuh), which does not happen on this problem.
     s.init_cells()
     s.zero_corrections()
+    clocks = ClockSampler(local)     # NVML initialisation (tens of ms, different on every rank) stays in front of the barrier
     barrier()
-    clocks = ClockSampler(local)
     clocks.start()
     n0 = s.launch_count()
     tr0 = s.slab_traffic() if world > 1 else None
