@@ -31,8 +31,8 @@
 //   LOCAL : all slabs in one process on one device and one stream (peer pointers are plain
 //           pointers; slab_p2p = 0 uses cudaMemcpyAsync). This is how the slab index arithmetic
 //           and the fused stores are tested on a single GPU.
-// Measured on B200s, 1024^3 fp32 (profiles/r2_bench_n*): 868 / 1568 / 2462 units/s on 2 / 4 / 8 GPUs vs 387 on one GPU
-// of the same box = efficiency 1.12 / 1.01 / 0.795 (round 1, slower single-GPU kernel: 1733 vs 261 = 0.83 at 8;
+// Measured on B200s, 1024^3 fp32 (profiles/r2_bench_n*): 897 / 1663 / 2795 units/s on 2 / 4 / 8 GPUs vs 405-407 on one GPU
+// of the same box = efficiency 1.10 / 1.02 / 0.863 (round 1, slower single-GPU kernel: 1733 vs 261 at 8;
 // NCCL send/recv then: 1324; fused + separate handshake kernels: 1400). DESIGN.md section 7 has the breakdown.
 #pragma once
 #include <cuda_runtime.h>
