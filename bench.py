@@ -150,6 +150,24 @@ class ClockSampler:
                 pass
             time.sleep(0.02)
 
+    def nvlink_kib(self):
+        """NVLink data payload counters of this GPU, summed over its links, in KiB since the driver was loaded
+        (NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX / _RX); None where NVML does not provide them."""
+        if not self.nv:
+            return None
+        try:
+            nv = self.nv
+            ids = [getattr(nv, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX", 138), getattr(nv, "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_RX", 139)]
+            vals = nv.nvmlDeviceGetFieldValues(self.h, [(i, 0xFFFFFFFF) for i in ids])   # scope: all links
+            out = []
+            for v in vals:
+                if v.nvmlReturn != 0:
+                    return None
+                out.append(int(v.value.ullVal))
+            return out
+        except Exception:
+            return None
+
     def start(self):
         if self.nv:
             self._t = threading.Thread(target=self._loop, daemon=True)
@@ -446,6 +464,7 @@ def run_ours(args):
     clocks.start()
     n0 = s.launch_count()
     tr0 = s.slab_traffic() if world > 1 else None
+    nvl_hw0 = clocks.nvlink_kib() if world > 1 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     with torch.cuda.stream(stream):
         if world > 1:
@@ -471,12 +490,18 @@ def run_ours(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
         tr1 = s.slab_traffic()
+        nvl_hw1 = clocks.nvlink_kib()
         per_step = (tr1["peer_store_bytes"] - tr0["peer_store_bytes"]) / (args.steps + 1)    # + the skew-absorbing cycle
         tb = torch.tensor([per_step], device="cuda", dtype=torch.float64)
         dist.all_reduce(tb, op=dist.ReduceOp.SUM)
         nvl = {"peer_store_bytes_per_step_this_rank": per_step, "peer_store_bytes_per_step_all_ranks": float(tb.item()),
                "gbs_per_gpu_out": per_step / (ms / args.steps * 1e-3) / 1e9,
                "explicit_exchange_bytes_in_timed_region": tr1["exchange_bytes"] - tr0["exchange_bytes"],
+               "hw_counter_tx_rx_bytes_per_step_this_rank": ([1024.0 * (b - a) / (args.steps + 1) for a, b in zip(nvl_hw0, nvl_hw1)]
+                                                              if nvl_hw0 and nvl_hw1 else None),
+               "hw_counter_source": "NVML_FI_DEV_NVLINK_THROUGHPUT_DATA_TX/_RX of this GPU, all links, read before and after the "
+                                    "timed cycles (payload KiB; includes the handshake words). On this pool NVML answers NOT_SUPPORTED "
+                                    "for these fields (probed on the B200 boxes), so the value is null here",
                "peak_per_direction_gbs": 770.0,
                "note": "bytes the smoother kernels store straight into other GPUs' memory (G = 4 boundary planes per neighbour "
                        "and pass, coarse boundary planes, the fused all-gather), counted per launch from the planes sent; "
