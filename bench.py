@@ -544,6 +544,11 @@ def run_ours(args):
     except Exception:
         pass
     traffic = traffic_tab.get(kname)
+    pipes = None
+    try:
+        pipes = json.load(open(os.path.join(ROOT, "profiles", "dram_traffic.json"))).get("_pipes", {}).get(key, {}).get(kname)
+    except Exception:
+        pass
     moved = traffic if traffic else comp_launch
     achieved = moved / (dom_ms * 1e-3) / 1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -555,6 +560,9 @@ def run_ours(args):
                 "effective_bytes_per_launch_A_op": aop_launch, "effective_gbs_A_op": aop_launch / (dom_ms * 1e-3) / 1e9,
                 "effective_frac_A_op": aop_launch / (dom_ms * 1e-3) / 1e9 / peak,
                 "share_of_step": dg["ms"] / total_prof, "peak_source": peak_src,
+                "binding_resource": ({"from": "ncu capture of this launch (profiles/, cold cache, not this run)", **pipes,
+                                      "reading": "the pass keeps the shared-memory data path busier than DRAM or the issue slots: "
+                                                 "it is bound by on-chip traffic per point and stage, not by HBM"} if pipes else None),
                 "frac_of_nominal_8000": achieved / NOMINAL_HBM_GBS,
                 "note": "frac is DRAM bytes moved / time / measured copy peak; the A_op figure (SURVEY 8(d)) counts the bytes the "
                         "un-fused reference operators would move and exceeds the peak by design of temporal blocking"}

@@ -133,7 +133,7 @@ def full(rep, tag, config):
             data.append(e)
     lines = [f"| launch | kernel | grid x block | time (ncu, cold) | DRAM read + write | compulsory | DRAM / compulsory | DRAM GB/s (% of {PEAK:.1f}) | "
              "issue slots busy | regs | smem wavefronts (conflict replays) | LSU-smem busy | L2 hit |", "|---|---|---|---|---|---|---|---|---|---|---|---|---|"]
-    traffic = {}
+    traffic, pipes = {}, {}
     c = 2.0 ** -dim
     for (kind, L, sw), e in zip(order, data):
         name = f"{kind}[L={L},sweeps={sw}]"
@@ -153,6 +153,9 @@ def full(rep, tag, config):
                      f"{int(m.get('launch__registers_per_thread', 0))} | {wf / 1e6:.1f} M ({100 * bc / max(wf, 1):.1f} %) | "
                      f"{100 * wf / 148 / cyc:.0f} % | {m.get('lts__t_sector_hit_rate.pct', 0):.0f} % |")
         traffic[name] = rd + wr
+        pipes[name] = {"issue_slots_busy_pct": round(m.get("smsp__issue_active.avg.pct_of_peak_sustained_active", 0), 1),
+                       "lsu_shared_memory_pipe_busy_pct": round(100 * wf / 148 / cyc, 1),
+                       "dram_pct_of_measured_peak": round((rd + wr) / t / 1e9 / PEAK * 100, 1)}
     summ = ""
     srcrep = os.path.join(os.path.dirname(rep), f"prof_{tag}_{config}_top.ncu-rep")
     if not os.path.exists(srcrep):
@@ -182,6 +185,9 @@ def full(rep, tag, config):
     except Exception:
         tab = {}
     tab[config] = traffic
+    allp = tab.get("_pipes", {})
+    allp[config] = pipes     # ncu, same capture: which unit of the SM the launch keeps busiest (bench.py: roofline.binding_resource)
+    tab["_pipes"] = allp
     src_note = tab.get("_source", {})
     if not isinstance(src_note, dict):
         src_note = {}
