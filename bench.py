@@ -20,7 +20,9 @@ Prints ONE JSON line (rank 0). Keys beyond the base contract:
                 the peak) is kept beside it as `effective_*`.
   vcycle        whole V-cycle: A_op effective bandwidth, the fused lower bound A_min, DRAM bytes per cycle
   cpu_baseline  the CPU oracle (C restatement of cpu-raw.lua) timed on this host
-  e2e           same metric through mg_step_host with pinned HOST buffers, copies timed
+  e2e           same metric through the C ABI with pinned HOST buffers, every step's copies inside the timed region:
+                `value` through mg_step_host_batch (independent host problems, the copies of neighbouring steps overlap
+                the cycle), `one_call_at_a_time` through mg_step_host (upload + cycle + download in sequence)
   parity        (--gpus N > 1) before timing: one V-cycle at 256^3 and at the timed 1024^3 slab shape, every rank's
                 slab of psi / Rs[L/2] / Vs[L/2] compared (CRC-32 of the bytes) with a single-GPU solver on rank 0;
                 a mismatch ends the run with a non-zero exit code
@@ -604,14 +606,40 @@ def run_ours(args):
         for _ in range(ne2e):
             s.step_host(fh.array, ph.array)
         torch.cuda.synchronize()
-        e2e_s = (time.perf_counter() - t0) / ne2e
+        serial_s = (time.perf_counter() - t0) / ne2e
+        # the same steps as a batch of independent host problems (mg_step_host_batch): every step still uploads its f and
+        # psi from pinned host memory and downloads its psi, but problem i+1's upload and problem i-1's download run on the
+        # two copy engines while problem i's cycle runs (PCIe is full duplex). One input f serves every problem; every
+        # problem has its own psi buffer (in: the point source, out: the result).
+        nb = max(4, min(2 * args.steps, 16 if world == 1 else 8))
+        pb = [pkg.PinnedArray((N,), dt) for _ in range(nb)]
+
+        def fill():
+            for a in pb:
+                a.array[...] = 0
+                a.array[N // 2] = 1.0 if rank == world // 2 else 0.0
+        fill()
+        s.step_host_batch([fh.array] * nb, [a.array for a in pb])  # warm: staging slots, streams
+        fill()
+        barrier()
+        t0 = time.perf_counter()
+        s.step_host_batch([fh.array] * nb, [a.array for a in pb])
+        torch.cuda.synchronize()
+        e2e_s = (time.perf_counter() - t0) / nb
+        for a in pb:
+            a.free()
         if dist is not None:
-            t = torch.tensor([e2e_s], device="cuda")
+            t = torch.tensor([e2e_s, serial_s], device="cuda")
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            e2e_s = float(t.item())
+            e2e_s, serial_s = float(t[0].item()), float(t[1].item())
         e2e = {"value": unit_scale / e2e_s, "unit": "V-cycles/s", "h2d_bytes_per_step": 2 * N * elem * world,
-               "d2h_bytes_per_step": (N * elem + 8) * world, "ms_per_step": e2e_s * 1e3, "steps": ne2e,
-               "api": "mg_step_host (upload f, psi; psiOld<-psi; V-cycle; err; download psi)"}
+               "d2h_bytes_per_step": (N * elem + 8) * world, "ms_per_step": e2e_s * 1e3, "steps": nb,
+               "api": "mg_step_host_batch: per step upload f, psi; psiOld<-psi; V-cycle; err; download psi -- a batch of "
+                      "independent host problems, the copies of neighbouring steps overlapped with the cycle on two copy streams",
+               "pcie_gbs_up": 2 * N * elem / e2e_s / 1e9, "pcie_gbs_down": N * elem / e2e_s / 1e9,
+               "one_call_at_a_time": {"value": unit_scale / serial_s, "ms_per_step": serial_s * 1e3, "steps": ne2e,
+                                      "api": "mg_step_host (upload f, psi; psiOld<-psi; V-cycle; err; download psi), "
+                                             "nothing overlapped: upload + cycle + download"}}
         fh.free()
         ph.free()
 

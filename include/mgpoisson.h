@@ -112,6 +112,11 @@ int mg_run(mg_ctx *ctx, int max_cycles, double accuracy, double *errs, int *n_do
                                                               /* cpu-raw.lua:239-258 */
 /* host-buffer entry point: upload f and psi, one mg_step, download psi. */
 int mg_step_host(mg_ctx *ctx, const void *f_host, void *psi_host, double *err);
+/* n independent problems in host memory (pinned: mg_host_alloc), each through mg_step_host's sequence, pipelined: while
+ * problem i's cycle runs, one copy engine uploads problem i+1 and the other downloads problem i-1 (cpu-gpu.lua:26-48 does
+ * these transfers one after the other around its device work). Same results as n calls of mg_step_host, bit for bit;
+ * psi_hosts[i] must be distinct buffers (f_hosts[i] may repeat); errs[i] = that problem's err (may be NULL). */
+int mg_step_host_batch(mg_ctx *ctx, int n, const void **f_hosts, void **psi_hosts, double *errs);
 /* true residual RMS ||f - A psi|| / sqrt(N) (not in the reference) */
 int mg_residual_norm(mg_ctx *ctx, double *rms);
 

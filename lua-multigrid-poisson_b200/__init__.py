@@ -103,6 +103,7 @@ def lib():
         "mg_step": (i, [vp, pd]),
         "mg_run": (i, [vp, i, d, pd, pi]),
         "mg_step_host": (i, [vp, vp, vp, pd]),
+        "mg_step_host_batch": (i, [vp, i, C.POINTER(vp), C.POINTER(vp), pd]),
         "mg_residual_norm": (i, [vp, pd]),
         "mg_twogrid": (i, [vp, d, vp, vp, i]),
         "mg_smooth": (i, [vp, i, vp, vp, d, i]),
@@ -355,6 +356,17 @@ class MultigridCUDA:
         e = C.c_double()
         self._ck(lib().mg_step_host(self._h, _hptr(f_host), _hptr(psi_host), C.byref(e)))
         return e.value
+
+    def step_host_batch(self, f_hosts, psi_hosts):
+        """mg_step_host for a list of independent host problems, transfers overlapped with the cycles
+        (psi_hosts are updated in place and must be distinct arrays); returns the list of errs."""
+        n = len(psi_hosts)
+        assert len(f_hosts) == n
+        fp = (C.c_void_p * max(n, 1))(*[_hptr(a) for a in f_hosts])
+        pp = (C.c_void_p * max(n, 1))(*[_hptr(a) for a in psi_hosts])
+        errs = (C.c_double * max(n, 1))()
+        self._ck(lib().mg_step_host_batch(self._h, n, fp, pp, errs))
+        return [errs[k] for k in range(n)]
 
     def run(self, max_cycles=None, accuracy=None):
         """cpu-raw.lua:239-258. Prints the reference's `#iter err` table; returns the errs."""

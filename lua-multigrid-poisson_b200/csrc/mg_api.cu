@@ -325,6 +325,81 @@ int mg_step_host(mg_ctx *ctx, const void *f_host, void *psi_host, double *err)
     return ctx->sync();
 }
 
+// n independent problems held in host memory, each taken through mg_step_host's sequence (upload f and psi; psiOld <- psi;
+// one V-cycle; err; download psi) -- but pipelined: problem i+1 is uploaded by one copy engine and problem i-1 downloaded
+// by the other while problem i's cycle runs, through two device staging slots per direction. PCIe is full duplex, so a
+// batch costs its uploads (2 fields per problem) instead of uploads + cycle + downloads. Results are bit-identical to n
+// calls of mg_step_host (same kernels, same order). Handles this covers: single GPU and one-process-per-GPU slabs (every
+// rank passes its own planes, all ranks the same n); other groups and the reference-sequence mode run the calls one by one.
+int mg_step_host_batch(mg_ctx *ctx, int n, const void **f_hosts, void **psi_hosts, double *errs)
+{
+    CTX_OR_FAIL(ctx);
+    if (n < 0 || (n > 0 && (!f_hosts || !psi_hosts))) return ctx->fail(MG_EINVAL, "mg_step_host_batch: bad argument");
+    for (int i = 0; i < n; ++i) {
+        if (!f_hosts[i] || !psi_hosts[i]) return ctx->fail(MG_EINVAL, "mg_step_host_batch: null host pointer");
+        for (int j = 0; j < i; ++j)   // an output buffer is written while later problems are still being read
+            if (psi_hosts[j] == psi_hosts[i]) return ctx->fail(MG_EINVAL, "mg_step_host_batch: psi buffers must be distinct");
+    }
+    const bool nccl = ctx->group && ctx->group->nccl;
+    if ((ctx->group && !nccl) || ctx->mode == MG_MODE_REFSEQ || n < 2) {
+        for (int i = 0; i < n; ++i) {
+            double e;
+            if (int rc = mg_step_host(ctx, f_hosts[i], psi_hosts[i], &e)) return rc;
+            if (errs) errs[i] = e;
+        }
+        return MG_OK;
+    }
+    const int top = ctx->nlevels - 1;
+    const size_t nb = (nccl ? ctx->own_elems(top) : ctx->N) * ctx->elem;
+    const size_t off = ctx->own_off_elems(top) * ctx->elem;
+    int rc = ctx->pipe_ensure(nb, n);
+    if (rc) return rc;
+    mg_ctx::HostPipe *p = ctx->pipe;
+    cudaStream_t st = ctx->stream;
+    auto body = [&]() -> int {
+        for (int i = 0; i < n; ++i) {
+            const int s = i & 1;
+            // copy engine 1: this problem's inputs into staging slot s (free once problem i-2 has left it)
+            if (i >= 2) MG_CK(ctx, cudaStreamWaitEvent(p->up, p->in_free[s], 0));
+            MG_CK(ctx, cudaMemcpyAsync(p->in_f[s], f_hosts[i], nb, cudaMemcpyHostToDevice, p->up));
+            MG_CK(ctx, cudaMemcpyAsync(p->in_u[s], psi_hosts[i], nb, cudaMemcpyHostToDevice, p->up));
+            MG_CK(ctx, cudaEventRecord(p->up_done[s], p->up));
+            // the cycle's stream: staging -> the solver's fields, one step, result -> staging
+            MG_CK(ctx, cudaStreamWaitEvent(st, p->up_done[s], 0));
+            MG_CK(ctx, cudaMemcpyAsync((char *)ctx->f + off, p->in_f[s], nb, cudaMemcpyDeviceToDevice, st));
+            MG_CK(ctx, cudaMemcpyAsync((char *)ctx->psi + off, p->in_u[s], nb, cudaMemcpyDeviceToDevice, st));
+            MG_CK(ctx, cudaEventRecord(p->in_free[s], st));
+            if (nccl) ctx->f_ghost_dirty = ctx->u_ghost_dirty = true;
+            MG_CK(ctx, cudaMemcpyAsync(ctx->psiOld, ctx->psi, ctx->Ntop * ctx->elem, cudaMemcpyDeviceToDevice, st));
+            if (int r = ctx->vcycle()) return r;
+            if (int r = ctx->eng->frob_partial_sum(ctx, nullptr)) return r;   // cpu-raw.lua:249-254, sum left on the device
+            if (nccl) {
+                mg::SlabGroup *g = ctx->group;
+                int e = g->api->AllReduce(ctx->d_scalar, ctx->d_scalar, 1, NcclApi::kFloat64, NcclApi::kSum, g->comm, st);
+                if (e) return ctx->fail(MG_ECUDA, g->api->GetErrorString(e));
+            }
+            MG_CK(ctx, cudaMemcpyAsync(p->h_sum + i, ctx->d_scalar, sizeof(double), cudaMemcpyDeviceToHost, st));
+            if (i >= 2) MG_CK(ctx, cudaStreamWaitEvent(st, p->out_free[s], 0));
+            MG_CK(ctx, cudaMemcpyAsync(p->out_u[s], (char *)ctx->psi + off, nb, cudaMemcpyDeviceToDevice, st));
+            MG_CK(ctx, cudaEventRecord(p->comp_done[s], st));
+            // copy engine 2: the result back to the caller
+            MG_CK(ctx, cudaStreamWaitEvent(p->down, p->comp_done[s], 0));
+            MG_CK(ctx, cudaMemcpyAsync(psi_hosts[i], p->out_u[s], nb, cudaMemcpyDeviceToHost, p->down));
+            MG_CK(ctx, cudaEventRecord(p->out_free[s], p->down));
+        }
+        return MG_OK;
+    };
+    rc = body();
+    // drain all three streams whatever happened, so that no copy is in flight when the caller gets its buffers back
+    cudaError_t e1 = cudaStreamSynchronize(p->up), e2 = cudaStreamSynchronize(st), e3 = cudaStreamSynchronize(p->down);
+    if (rc) return rc;
+    if (e1 != cudaSuccess || e2 != cudaSuccess || e3 != cudaSuccess)
+        return ctx->fail_cuda(e1 != cudaSuccess ? e1 : (e2 != cudaSuccess ? e2 : e3), "mg_step_host_batch");
+    if (errs)
+        for (int i = 0; i < n; ++i) errs[i] = std::sqrt(p->h_sum[i] / (double)ctx->N);
+    return ctx->sync();
+}
+
 int mg_residual_norm(mg_ctx *ctx, double *rms)
 {
     CTX_OR_FAIL(ctx);

@@ -9,6 +9,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <map>
+#include <new>
 #include <string>
 #include <tuple>
 #include <vector>
@@ -157,6 +158,18 @@ struct mg_ctx {
     bool peer_ipc = false, p2p = false, slab_graph_opt = true;
     unsigned long long *slab_trace = nullptr;   // timeline of the slab passes (option "slab_trace"; Stream3DArgs::trace)
     size_t Ntop = 0;                    // elements allocated for a top-level field (incl. ghosts)
+
+    // ---- pipelined host-buffer batches (mg_step_host_batch): the two copy engines run beside the cycle's stream
+    struct HostPipe {
+        cudaStream_t up = nullptr, down = nullptr;              // host -> device, device -> host
+        void *in_f[2] = {}, *in_u[2] = {}, *out_u[2] = {};      // two staging slots for each direction
+        cudaEvent_t up_done[2] = {}, in_free[2] = {}, comp_done[2] = {}, out_free[2] = {};
+        double *h_sum = nullptr;                                // pinned: sum (psi - psiOld)^2 of every problem of the batch
+        int cap = 0;
+        size_t nb = 0;
+    } *pipe = nullptr;
+    int pipe_ensure(size_t nb, int n);
+    void pipe_release();
 
     int planes(int lv) const { return dist[lv] ? nzl[lv] + 2 * G : (dim == 3 ? (1 << lv) : 1); }
     size_t plane_elems(int lv) const { size_t L = (size_t)1 << lv; return L * L; }
@@ -1414,6 +1427,7 @@ inline void mg_ctx::release()
     }
     drop_graph();
     if (own_stream) cudaStreamSynchronize(own_stream);
+    pipe_release();
     if (arena) cudaFree(arena);
     if (debug_arena) cudaFree(debug_arena);
     if (d_partial) cudaFree(d_partial);
@@ -1579,6 +1593,50 @@ inline int mg_ctx::copy_in(int which, int lv, const void *host, size_t bytes)
 inline int mg_ctx::copy_out(int which, int lv, void *host, size_t bytes)
 {
     return mg_copy_impl(this, which, lv, host, bytes, false);
+}
+
+inline void mg_ctx::pipe_release()
+{
+    if (!pipe) return;
+    if (pipe->up) { cudaStreamSynchronize(pipe->up); cudaStreamDestroy(pipe->up); }
+    if (pipe->down) { cudaStreamSynchronize(pipe->down); cudaStreamDestroy(pipe->down); }
+    for (int s = 0; s < 2; ++s) {
+        if (pipe->in_f[s]) cudaFree(pipe->in_f[s]);
+        if (pipe->in_u[s]) cudaFree(pipe->in_u[s]);
+        if (pipe->out_u[s]) cudaFree(pipe->out_u[s]);
+        for (cudaEvent_t e : {pipe->up_done[s], pipe->in_free[s], pipe->comp_done[s], pipe->out_free[s]})
+            if (e) cudaEventDestroy(e);
+    }
+    if (pipe->h_sum) cudaFreeHost(pipe->h_sum);
+    delete pipe;
+    pipe = nullptr;
+}
+
+// staging slots, copy streams and events of mg_step_host_batch, created on first use (3 x 2 fields of nb bytes)
+inline int mg_ctx::pipe_ensure(size_t nb, int n)
+{
+    if (pipe && pipe->nb != nb) pipe_release();
+    if (!pipe) {
+        pipe = new (std::nothrow) HostPipe();
+        if (!pipe) return fail(MG_ENOMEM, "out of host memory");
+        pipe->nb = nb;
+        MG_CK(this, cudaStreamCreateWithFlags(&pipe->up, cudaStreamNonBlocking));
+        MG_CK(this, cudaStreamCreateWithFlags(&pipe->down, cudaStreamNonBlocking));
+        for (int s = 0; s < 2; ++s) {
+            MG_CK(this, cudaMalloc(&pipe->in_f[s], nb));
+            MG_CK(this, cudaMalloc(&pipe->in_u[s], nb));
+            MG_CK(this, cudaMalloc(&pipe->out_u[s], nb));
+            for (cudaEvent_t *e : {&pipe->up_done[s], &pipe->in_free[s], &pipe->comp_done[s], &pipe->out_free[s]})
+                MG_CK(this, cudaEventCreateWithFlags(e, cudaEventDisableTiming));
+        }
+    }
+    if (pipe->cap < n) {
+        if (pipe->h_sum) cudaFreeHost(pipe->h_sum);
+        pipe->h_sum = nullptr; pipe->cap = 0;
+        MG_CK(this, cudaMallocHost((void **)&pipe->h_sum, sizeof(double) * (size_t)n));
+        pipe->cap = n;
+    }
+    return MG_OK;
 }
 
 inline void mg_ctx::drop_graph()

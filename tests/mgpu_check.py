@@ -19,6 +19,7 @@ from __graft_entry__ import load_package  # noqa: E402
 
 def main():
     size = int(sys.argv[1]) if len(sys.argv) > 1 else 256
+    only = sys.argv[2] if len(sys.argv) > 2 else ""     # "batch": only the host-batch check (short GPU calls)
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -27,6 +28,8 @@ def main():
     # (real kind, fused transport, smooth): smooth = 4 and 8 give an odd number of ping-pong passes per level visit
     # unless the slab schedule pads them; the default 7 gives an even one
     for real, p2p, smooth in (("float", True, 7), ("double", True, 7), ("float", False, 7), ("float", True, 4), ("float", True, 8)):
+        if only:
+            break
         s = pkg.create_distributed(size, real, dim=3, p2p=p2p, smooth=smooth)
         errs = [s.step() for _ in range(3)]
         rn = s.residual_norm()
@@ -50,6 +53,8 @@ def main():
     # conjugate gradient on slabs (mg_cg): ghost planes of p by ncclSend/ncclRecv, scalars all-reduced; compared with the
     # single-GPU run (same algorithm, different summation order: iteration counts equal, histories to 1e-9)
     for real in ("double",):
+        if only:
+            break
         s = pkg.create_distributed(size, real, dim=3)
         errs, linf = s.conjgrad(max_iter=60, epsilon=1e-6)
         if rank == 0:
@@ -65,6 +70,43 @@ def main():
         e_after = s.step()
         ok = ok and bool(np.isfinite(e_after))
         s.close()
+    # pipelined host batches on slabs (mg_step_host_batch: every rank passes its own planes of each problem): against
+    # the single-GPU solver fed the whole fields through mg_step_host, one problem at a time
+    def gather(a):
+        mine = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+        parts = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(parts, mine)
+        return torch.cat(parts, 0).cpu().numpy()
+    s = pkg.create_distributed(size, "float", dim=3)
+    f0, p0 = s.f.download(), s.psi.download()
+    nprob = 4
+    fs = [pkg.PinnedArray(f0.shape, np.float32) for _ in range(nprob)]
+    ps = [pkg.PinnedArray(f0.shape, np.float32) for _ in range(nprob)]
+    for k in range(nprob):
+        fs[k].array[...] = f0 * np.float32(1 + 0.25 * k)
+        ps[k].array[...] = p0 * np.float32(1 - 0.125 * k)
+    gf = [gather(a.array) for a in fs]
+    gp = [gather(a.array) for a in ps]
+    errs = s.step_host_batch([a.array for a in fs], [a.array for a in ps])
+    got = [gather(a.array) for a in ps]
+    if rank == 0:
+        one = pkg.MultigridCUDA(size, "float", dim=3, out=False, device=local)
+        one.set_tuning(tb=4)
+        one.set_option("stream_min_L", 64)
+        bok, e1 = True, []
+        for k in range(nprob):
+            fh, ph = pkg.PinnedArray(gf[k].shape, np.float32), pkg.PinnedArray(gf[k].shape, np.float32)
+            fh.array[...] = gf[k]; ph.array[...] = gp[k]
+            e1.append(one.step_host(fh.array, ph.array))
+            bok = bok and ph.array.tobytes() == got[k].tobytes() and abs(errs[k] - e1[-1]) <= 1e-9 * abs(e1[-1])
+            fh.free(); ph.free()
+        print(f"[mgpu_check] {world} GPUs, {size}^3 float, {nprob} host problems pipelined through mg_step_host_batch on slabs: "
+              f"err {errs} vs {e1}; psi bit-identical to 1 GPU: {bok}", flush=True)
+        ok = ok and bok
+        one.close()
+    for a in fs + ps:
+        a.free()
+    s.close()
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     dist.destroy_process_group()

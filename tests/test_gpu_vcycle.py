@@ -233,6 +233,48 @@ def test_host_buffer_entry_point(mgp, orc):
     f.free(); psi.free(); s.close()
 
 
+@pytest.mark.parametrize("dim,size,real", [(3, 64, "float"), (2, 256, "double"), (3, 128, "float")])
+def test_pipelined_host_batch_equals_one_call_at_a_time(mgp, orc, dim, size, real):
+    """mg_step_host_batch (uploads, cycles and downloads overlapped on three streams, two staging slots per direction):
+    every problem's psi and err equal what mg_step_host gives for it alone, and the oracle's for the first problem.
+    The problems differ (scaled right-hand sides, shifted sources), so a mixed-up staging slot cannot pass."""
+    dt = np.float64 if real == "double" else np.float32
+    shape = (size,) * dim
+    n = 5
+    o = orc.Oracle(size, real, dim, nthreads=8)
+    f0, p0 = np.array(o.f, dtype=dt).reshape(shape), np.array(o.psi, dtype=dt).reshape(shape)
+    fs = [mgp.PinnedArray(shape, dt) for _ in range(n)]
+    ps = [mgp.PinnedArray(shape, dt) for _ in range(n)]
+    want = []
+    s = mgp.MultigridCUDA(size, real, dim=dim, out=False)
+    for k in range(n):
+        fs[k].array[...] = f0 * dt(1 + 0.25 * k)
+        ps[k].array[...] = np.roll(p0, k, axis=0) * dt(1 - 0.125 * k)
+    one = mgp.PinnedArray(shape, dt)
+    for k in range(n):      # the serial entry point, one problem at a time, on the same handle (the coarse
+        one.array[...] = ps[k].array     # corrections Vs persist from call to call: same sequence in both runs)
+        want.append((s.step_host(fs[k].array, one.array), one.array.copy()))
+    s.close()
+    s = mgp.MultigridCUDA(size, real, dim=dim, out=False)
+    errs = s.step_host_batch([a.array for a in fs], [a.array for a in ps])
+    for k in range(n):
+        assert errs[k] == want[k][0], (k, errs[k], want[k][0])
+        assert_bits_equal(ps[k].array, want[k][1], f"problem {k} of the batch")
+    eo = o.step()
+    assert abs(errs[0] - eo) <= err_rtol(size ** dim) * eo
+    assert_bits_equal(ps[0].array, o.psi, "first problem of the batch against the oracle")
+    # second batch on the same handle (slots and events are reused), n = 2 and the degenerate sizes
+    errs2 = s.step_host_batch([fs[0].array, fs[1].array], [ps[0].array, ps[1].array])
+    assert len(errs2) == 2 and all(np.isfinite(errs2))
+    assert s.step_host_batch([], []) == []
+    assert len(s.step_host_batch([fs[2].array], [ps[2].array])) == 1
+    with pytest.raises(mgp.MGError):
+        s.step_host_batch([fs[0].array, fs[0].array], [ps[0].array, ps[0].array])   # outputs must be distinct
+    for a in fs + ps + [one]:
+        a.free()
+    s.close()
+
+
 def test_fp32_arithmetic_within_stated_tolerance_of_cpu_raw_float(mgp, orc):
     """north_star: fp32 ~1e-5 relative to the initial residual.
     MG_REAL_F32 (fp32 arithmetic, gpu.lua float semantics) against cpu-raw.lua's float mode
