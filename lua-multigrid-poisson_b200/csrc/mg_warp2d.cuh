@@ -36,7 +36,28 @@
 #define MG_PACKED_F32 1       // fp32 stage arithmetic with Blackwell's packed FADD2/FFMA2/FMUL2
 #endif
 
+// Cache prefetch of the rows a warp will need a few steps from now (f for stage 1 -- its first touch is a DRAM/L2 miss on
+// the row-to-row critical path -- and, where the source row is not fetched ahead in registers (fp64), the source row):
+// 0 off, 1 prefetch.global.L1, 2 prefetch.global.L2. MG_W2D_PFD = how many rows ahead.
+#ifndef MG_W2D_PF
+#define MG_W2D_PF 0
+#endif
+#ifndef MG_W2D_PFD
+#define MG_W2D_PFD 2
+#endif
+
 namespace mg {
+
+__device__ __forceinline__ void w2d_prefetch(const void *p)
+{
+#if MG_W2D_PF == 1
+    asm volatile("prefetch.global.L1 [%0];" ::"l"(p));
+#elif MG_W2D_PF == 2
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+#else
+    (void)p;
+#endif
+}
 
 template <typename T> __device__ __forceinline__ T shfl_up1(T v) { return __shfl_up_sync(0xffffffffu, v, 1); }
 template <typename T> __device__ __forceinline__ T shfl_dn1(T v) { return __shfl_down_sync(0xffffffffu, v, 1); }
@@ -126,6 +147,12 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
     auto step = [&](auto steady_tag, auto masked_tag, const int t) {
         constexpr bool ST = decltype(steady_tag)::value, MK = decltype(masked_tag)::value;
         const int q = yb + t;
+        if (MG_W2D_PF != 0 && xin) {
+            const int qf = q - 1 + MG_W2D_PFD;               // stage 1 completes row q - 1 now
+            if (qf >= 0 && qf < L) w2d_prefetch(f + (size_t)gx0 + sL * (size_t)qf);
+            const int qs = q + MG_W2D_PFD + (PREFETCH ? 1 : 0);
+            if (qs >= 0 && qs < L) w2d_prefetch(src + (size_t)gx0 + sL * (size_t)qs);
+        }
         if (!PREFETCH) fetch(q, ST ? (!MK || xin) : (xin && q >= 0 && q < L));
         R row[4];
 #pragma unroll
