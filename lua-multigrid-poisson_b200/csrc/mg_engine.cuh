@@ -844,7 +844,10 @@ template <typename R, typename A, int DIM> struct EngineT : Engine {
         TY &= ~1;
         const int nitems = nstrips * ((L + TY - 1) / TY);
         c->prof_begin(PRO ? MG_K_SWEEP_PROLONG : (RES ? MG_K_SWEEP_RESTRICT : MG_K_SWEEP), L, S);
-        MG_CK(c, launch_k(c, k_warp2d<R, A, S, PRO, RES>, dim3((unsigned)((nitems + 3) / 4)), dim3(128), 0, dst, src, f, Vp, Rout, L, TY, nstrips, nitems, cf));
+        auto kern = k_warp2d<R, A, S, PRO, RES>;
+        constexpr int smem = C::template smem_bytes<R, A>();   // the warps' f (and source) row rings
+        if (smem > 48 * 1024) MG_CK(c, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        MG_CK(c, launch_k(c, kern, dim3((unsigned)((nitems + 3) / 4)), dim3(128), (size_t)smem, dst, src, f, Vp, Rout, L, TY, nstrips, nitems, cf));
         c->prof_end();
         MG_LAUNCH_CHECK(c);
         return MG_OK;

@@ -46,7 +46,66 @@
 #define MG_W2D_PFD 2
 #endif
 
+// f rows through a per-warp shared-memory ring filled by cp.async (LDGSTS): every f row is fetched from global memory ONCE,
+// MG_W2D_PFROWS rows before stage 1 needs it and without holding registers, and the NST stages read it back with LDS (a
+// lane only ever reads the 16-byte chunks it copied itself, so cp.async.wait_group is all the synchronisation there is).
+// Before: NST global loads of the row (one miss + NST - 1 L1 hits), the miss on the row-to-row critical path.
+// Where the source row is not fetched ahead in registers (8-byte accumulators) it takes the same route.
+#ifndef MG_W2D_RING
+#define MG_W2D_RING 1         // 0 off, 1 4-byte reals only, 2 every real kind
+#endif
+#ifndef MG_W2D_SRCRING
+#define MG_W2D_SRCRING 2      // source rows (and, PRO, their coarse values) through rings too: 0 never, 1 where they are not
+                              // fetched ahead in registers (8-byte accumulators), 2 always (no register prefetch at all)
+#endif
+#ifndef MG_W2D_PFROWS
+#define MG_W2D_PFROWS 3
+#endif
+
 namespace mg {
+
+constexpr int w2d_pow2ceil(int x) { int p = 1; while (p < x) p <<= 1; return p; }
+
+// 16 bytes global -> shared, asynchronously; nbytes = 0 writes zeros (rows / columns outside the grid)
+__device__ __forceinline__ void cp_async16(uint32_t saddr, const void *g, uint32_t nbytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(saddr), "l"(g), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async8(uint32_t saddr, const void *g, uint32_t nbytes)
+{
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" ::"r"(saddr), "l"(g), "r"(nbytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// one lane's four values of a ring row: fp32 one 16-byte chunk at lane*16; fp64 two, the second 512 bytes further on
+// (both layouts are bank-conflict free for 128-bit accesses)
+template <typename R> __device__ __forceinline__ void ring_copy(uint32_t saddr, const R *g, bool ok)
+{
+    cp_async16(saddr, g, ok ? 16u : 0u);
+    if (sizeof(R) == 8) cp_async16(saddr + 512u, g + 2, ok ? 16u : 0u);
+}
+__device__ __forceinline__ void ring_read(uint32_t saddr, float *o)
+{
+    asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(o[0]), "=f"(o[1]), "=f"(o[2]), "=f"(o[3]) : "r"(saddr));
+}
+__device__ __forceinline__ void ring_read(uint32_t saddr, double *o)
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(saddr));
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2+512];" : "=d"(o[2]), "=d"(o[3]) : "r"(saddr));
+}
+
+// a lane's two coarse values (PRO): 8 bytes (fp32) or 16 (fp64) per lane and coarse row
+__device__ __forceinline__ void ring_copy2(uint32_t saddr, const float *g, bool ok) { cp_async8(saddr, g, ok ? 8u : 0u); }
+__device__ __forceinline__ void ring_copy2(uint32_t saddr, const double *g, bool ok) { cp_async16(saddr, g, ok ? 16u : 0u); }
+__device__ __forceinline__ void ring_read2(uint32_t saddr, float *o)
+{
+    asm volatile("ld.shared.v2.f32 {%0, %1}, [%2];" : "=f"(o[0]), "=f"(o[1]) : "r"(saddr));
+}
+__device__ __forceinline__ void ring_read2(uint32_t saddr, double *o)
+{
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(o[0]), "=d"(o[1]) : "r"(saddr));
+}
 
 __device__ __forceinline__ void w2d_prefetch(const void *p)
 {
@@ -89,6 +148,22 @@ template <int S, bool RES> struct Warp2DCfg {
     static constexpr int H = NST;
     static constexpr int HX = (H + 3) / 4 * 4;
     static constexpr int TXU = 128 - 2 * HX;  // columns stored per warp
+    // shared-memory rings (MG_W2D_RING): f rows q - NST .. q - 1 + PF are live at step q, source rows q .. q + PF
+    static constexpr int PF = MG_W2D_PFROWS;
+    static constexpr int FRING = w2d_pow2ceil(NST + PF);
+    static constexpr int SRING = w2d_pow2ceil(PF + 1);
+    template <typename R> static constexpr bool f_ring() { return MG_W2D_RING == 2 || (MG_W2D_RING == 1 && sizeof(R) == 4); }
+    template <typename R, typename A> static constexpr bool src_ring()
+    {
+        return f_ring<R>() && (MG_W2D_SRCRING == 2 || (MG_W2D_SRCRING == 1 && sizeof(A) != 4));
+    }
+    template <typename R, typename A> static constexpr int warp_bytes()
+    {
+        // f rows, source rows, and (PRO) the coarse values of the source rows: 2 per lane and row
+        return f_ring<R>() ? (FRING + (src_ring<R, A>() ? SRING : 0)) * 128 * (int)sizeof(R) +
+                                 (src_ring<R, A>() ? SRING * 64 * (int)sizeof(R) : 0) : 0;
+    }
+    template <typename R, typename A> static constexpr int smem_bytes() { return 4 * warp_bytes<R, A>(); }
 };
 
 template <typename R, typename A, int S, bool PRO, bool RES>
@@ -115,6 +190,35 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
     // the strip (with its halo columns) lies inside the grid: no column masks
     const bool strip_inner = (x0 - C::HX >= 0) && (x0 - C::HX + 128 <= L);
 
+    constexpr bool RING = C::template f_ring<R>();
+    constexpr bool SRCRING = C::template src_ring<R, A>();
+    constexpr int ROWB = 128 * (int)sizeof(R), PF = C::PF;
+    extern __shared__ __align__(16) unsigned char w2d_smem[];
+    // this lane's chunk of row slot 0 of its warp's f ring; the source ring follows the f ring
+    const uint32_t fring = RING ? (uint32_t)__cvta_generic_to_shared(w2d_smem) +
+                                      (uint32_t)((threadIdx.x >> 5) * C::template warp_bytes<R, A>() + lane * 16) : 0u;
+    const uint32_t sring = fring + (uint32_t)(C::FRING * ROWB);
+    constexpr int VROWB = 64 * (int)sizeof(R);
+    const uint32_t vring = sring + (uint32_t)(C::SRING * ROWB) - (uint32_t)(lane * 16) + (uint32_t)(lane * 2 * (int)sizeof(R));
+    // request f row `qf` (and, SRCRING, source row `qs`) as one cp.async group
+    auto request = [&](const int qf, const int qs) {
+        if (RING) {
+            const bool okf = xin && qf >= 0 && qf < L;
+            ring_copy<R>(fring + (uint32_t)((qf & (C::FRING - 1)) * ROWB), okf ? f + (size_t)gx0 + sL * (size_t)qf : f, okf);
+            if (SRCRING) {
+                const bool oks = xin && qs >= 0 && qs < L;
+                ring_copy<R>(sring + (uint32_t)((qs & (C::SRING - 1)) * ROWB), oks ? src + (size_t)gx0 + sL * (size_t)qs : src, oks);
+                if (PRO)
+                    ring_copy2(vring + (uint32_t)((qs & (C::SRING - 1)) * VROWB),
+                               oks ? Vp + (size_t)(gx0 >> 1) + (size_t)L2 * (size_t)(qs >> 1) : Vp, oks);
+            }
+            cp_async_commit();
+        }
+    };
+    // before step 0: f rows yb - 1 .. yb - 2 + PF and source rows yb .. yb + PF - 1 (step t then requests yb + t - 1 + PF / yb + t + PF)
+#pragma unroll
+    for (int k = 0; k < PF; ++k) request(yb - 1 + k, yb + k);
+
     A acc[NST][4], prev[NST][4];
 #pragma unroll
     for (int s = 0; s < NST; ++s)
@@ -126,13 +230,16 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
     // step computes, so the global-load latency leaves the row-to-row critical path (+3 % at 4096^2, +10 % on
     // the PRO pass). With 8-byte accumulators the extra registers spill (-5 % at 2048^2 fp64): there the row is
     // fetched at the start of its own step.
-    constexpr bool PREFETCH = sizeof(A) == 4;
+    constexpr bool PREFETCH = sizeof(A) == 4 && !C::template src_ring<R, A>();
     R pre[4] = {(R)0, (R)0, (R)0, (R)0}, pv[2] = {(R)0, (R)0};
     auto fetch = [&](const int q, const bool ok) {
 #pragma unroll
         for (int i = 0; i < 4; ++i) pre[i] = (R)0;
         pv[0] = pv[1] = (R)0;
-        if (ok) {
+        if (SRCRING) {                                                                    // zero-filled outside the grid
+            ring_read(sring + (uint32_t)((q & (C::SRING - 1)) * ROWB), pre);
+            if (PRO) ring_read2(vring + (uint32_t)((q & (C::SRING - 1)) * VROWB), pv);
+        } else if (ok) {
             load4<R>(src + (size_t)gx0 + sL * (size_t)q, pre);
             if (PRO) {
                 const R *vp = Vp + (size_t)(gx0 >> 1) + (size_t)L2 * (size_t)(q >> 1);
@@ -153,6 +260,10 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
             const int qs = q + MG_W2D_PFD + (PREFETCH ? 1 : 0);
             if (qs >= 0 && qs < L) w2d_prefetch(src + (size_t)gx0 + sL * (size_t)qs);
         }
+        if (RING) {
+            request(q - 1 + PF, q + PF);
+            cp_async_wait<PF>();          // everything but the PF newest groups has landed: f row q - 1, source row q
+        }
         if (!PREFETCH) fetch(q, ST ? (!MK || xin) : (xin && q >= 0 && q < L));
         R row[4];
 #pragma unroll
@@ -168,7 +279,11 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
             const bool keep = pin && (MK ? xin : true);
             const bool is_res = RES && s == NST;
             R fv[4] = {(R)0, (R)0, (R)0, (R)0};
-            if (emit && keep) load4<R>(f + (size_t)gx0 + sL * (size_t)p, fv);
+            if (RING) {
+                if (emit) ring_read(fring + (uint32_t)((p & (C::FRING - 1)) * ROWB), fv);   // zeros outside the grid
+            } else if (emit && keep) {
+                load4<R>(f + (size_t)gx0 + sL * (size_t)p, fv);
+            }
             const R lft = shfl_up1(row[3]), rgt = shfl_dn1(row[0]);
             A o[4];
             if constexpr (PACKED) {
@@ -244,6 +359,7 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
         for (; t <= t_hi; ++t) step(std::true_type{}, std::true_type{}, t);
     }
     for (; t < nin; ++t) step(std::false_type{}, std::true_type{}, t);
+    if (RING) cp_async_wait<0>();
 }
 
 }  // namespace mg
