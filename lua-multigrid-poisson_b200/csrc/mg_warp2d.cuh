@@ -58,6 +58,9 @@
 #define MG_W2D_SRCRING 2      // source rows (and, PRO, their coarse values) through rings too: 0 never, 1 where they are not
                               // fetched ahead in registers (8-byte accumulators), 2 always (no register prefetch at all)
 #endif
+#ifndef MG_W2D_SRC64
+#define MG_W2D_SRC64 0        // 8-byte reals: 1 = the source rows (and PRO's coarse values) through a ring although f stays on L1 loads
+#endif
 #ifndef MG_W2D_PFROWS
 #define MG_W2D_PFROWS 3
 #endif
@@ -155,13 +158,14 @@ template <int S, bool RES> struct Warp2DCfg {
     template <typename R> static constexpr bool f_ring() { return MG_W2D_RING == 2 || (MG_W2D_RING == 1 && sizeof(R) == 4); }
     template <typename R, typename A> static constexpr bool src_ring()
     {
-        return f_ring<R>() && (MG_W2D_SRCRING == 2 || (MG_W2D_SRCRING == 1 && sizeof(A) != 4));
+        return (f_ring<R>() && (MG_W2D_SRCRING == 2 || (MG_W2D_SRCRING == 1 && sizeof(A) != 4))) ||
+               (MG_W2D_SRC64 != 0 && sizeof(R) == 8);
     }
     template <typename R, typename A> static constexpr int warp_bytes()
     {
         // f rows, source rows, and (PRO) the coarse values of the source rows: 2 per lane and row
-        return f_ring<R>() ? (FRING + (src_ring<R, A>() ? SRING : 0)) * 128 * (int)sizeof(R) +
-                                 (src_ring<R, A>() ? SRING * 64 * (int)sizeof(R) : 0) : 0;
+        return (f_ring<R>() ? FRING * 128 * (int)sizeof(R) : 0) +
+               (src_ring<R, A>() ? SRING * (128 + 64) * (int)sizeof(R) : 0);
     }
     template <typename R, typename A> static constexpr int smem_bytes() { return 4 * warp_bytes<R, A>(); }
 };
@@ -195,16 +199,19 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
     constexpr int ROWB = 128 * (int)sizeof(R), PF = C::PF;
     extern __shared__ __align__(16) unsigned char w2d_smem[];
     // this lane's chunk of row slot 0 of its warp's f ring; the source ring follows the f ring
-    const uint32_t fring = RING ? (uint32_t)__cvta_generic_to_shared(w2d_smem) +
-                                      (uint32_t)((threadIdx.x >> 5) * C::template warp_bytes<R, A>() + lane * 16) : 0u;
-    const uint32_t sring = fring + (uint32_t)(C::FRING * ROWB);
+    constexpr bool ANYRING = RING || SRCRING;
+    const uint32_t fring = ANYRING ? (uint32_t)__cvta_generic_to_shared(w2d_smem) +
+                                         (uint32_t)((threadIdx.x >> 5) * C::template warp_bytes<R, A>() + lane * 16) : 0u;
+    const uint32_t sring = fring + (uint32_t)(RING ? C::FRING * ROWB : 0);
     constexpr int VROWB = 64 * (int)sizeof(R);
     const uint32_t vring = sring + (uint32_t)(C::SRING * ROWB) - (uint32_t)(lane * 16) + (uint32_t)(lane * 2 * (int)sizeof(R));
     // request f row `qf` (and, SRCRING, source row `qs`) as one cp.async group
     auto request = [&](const int qf, const int qs) {
-        if (RING) {
-            const bool okf = xin && qf >= 0 && qf < L;
-            ring_copy<R>(fring + (uint32_t)((qf & (C::FRING - 1)) * ROWB), okf ? f + (size_t)gx0 + sL * (size_t)qf : f, okf);
+        if (ANYRING) {
+            if (RING) {
+                const bool okf = xin && qf >= 0 && qf < L;
+                ring_copy<R>(fring + (uint32_t)((qf & (C::FRING - 1)) * ROWB), okf ? f + (size_t)gx0 + sL * (size_t)qf : f, okf);
+            }
             if (SRCRING) {
                 const bool oks = xin && qs >= 0 && qs < L;
                 ring_copy<R>(sring + (uint32_t)((qs & (C::SRING - 1)) * ROWB), oks ? src + (size_t)gx0 + sL * (size_t)qs : src, oks);
@@ -260,7 +267,7 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
             const int qs = q + MG_W2D_PFD + (PREFETCH ? 1 : 0);
             if (qs >= 0 && qs < L) w2d_prefetch(src + (size_t)gx0 + sL * (size_t)qs);
         }
-        if (RING) {
+        if (ANYRING) {
             request(q - 1 + PF, q + PF);
             cp_async_wait<PF>();          // everything but the PF newest groups has landed: f row q - 1, source row q
         }
@@ -359,7 +366,7 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
         for (; t <= t_hi; ++t) step(std::true_type{}, std::true_type{}, t);
     }
     for (; t < nin; ++t) step(std::false_type{}, std::true_type{}, t);
-    if (RING) cp_async_wait<0>();
+    if (ANYRING) cp_async_wait<0>();
 }
 
 }  // namespace mg
