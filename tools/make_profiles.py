@@ -205,7 +205,7 @@ def sass(tag):
         m = re.match(r"\s+/\*[0-9a-f]+\*/\s+(?:@!?U?P\d+\s+)?([A-Z0-9_.]+)", line)
         if m:
             ops[m.group(1).split(".")[0]] += 1
-    want = ["UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "FADD2", "FFMA2", "FMUL2", "LDS", "STS", "SHFL", "LDTM", "STTM", "LDG", "STG",
+    want = ["UTMALDG", "UTMASTG", "UBLKCP", "SYNCS", "FADD2", "FFMA2", "FMUL2", "LDS", "STS", "SHFL", "LDTM", "STTM", "LDG", "LDGSTS", "LDGDEPBAR", "STG",
             "DADD", "DFMA", "DMUL", "HMMA", "BAR", "ST", "LD", "ATOMG", "RED", "VIMNMX3", "MUFU"]
     log = os.path.join(ROOT, "lua-multigrid-poisson_b200", "csrc", "build.log")
     spills = regs = ""
