@@ -10,9 +10,13 @@
 // streams down the rows. The S sweeps (+ the residual stage) are a register pipeline: a row
 // leaves stage s and enters stage s+1 in the same step, in registers; x-neighbours across
 // lanes come from __shfl_up/down, the y-1 neighbour is the previous row (register `prev`),
-// the y+1 neighbour completes the pending sum `acc` one step later. No shared memory, no
-// __syncthreads(), no intermediate field ever touches L2/HBM. The summation order
-// ((xl+xr)+yl)+yr of the reference is preserved => bit-identical to one sweep per launch.
+// the y+1 neighbour completes the pending sum `acc` one step later. No __syncthreads(), no
+// intermediate field ever touches L2/HBM. The summation order ((xl+xr)+yl)+yr of the reference is
+// preserved => bit-identical to one sweep per launch.
+// 4-byte reals: the rows a warp reads from global memory (f, the source, PRO's coarse values) arrive
+// through per-warp shared-memory rings filled by cp.async three rows ahead (MG_W2D_RING below); every
+// lane reads back only what it copied itself, so the rings need no barrier either. 8-byte reals read
+// their rows with plain (L1-cached) loads: the rings measured slower there.
 // fp32 arithmetic is issued as packed FADD2 / FFMA2 / FMUL2 (two IEEE-rn operations per issue slot); the
 // rows where every stage is active and inside the grid run a predicate-free body.
 // (MEASURED: making the stages of a step independent -- stage s+1 consuming what stage s emitted a
@@ -233,10 +237,10 @@ k_warp2d(R *__restrict__ dst, const R *__restrict__ src, const R *__restrict__ f
         for (int i = 0; i < 4; ++i) { acc[s][i] = (A)0; prev[s][i] = (A)0; }
     A rpart[2] = {(A)0, (A)0};
 
-    // fp32 arithmetic: the source row (and, PRO, its two coarse values) of the NEXT step is fetched while this
-    // step computes, so the global-load latency leaves the row-to-row critical path (+3 % at 4096^2, +10 % on
-    // the PRO pass). With 8-byte accumulators the extra registers spill (-5 % at 2048^2 fp64): there the row is
-    // fetched at the start of its own step.
+    // Without a source ring and with fp32 arithmetic the source row (and, PRO, its two coarse values) of the NEXT
+    // step is fetched while this step computes, so the global-load latency leaves the row-to-row critical path
+    // (+3 % at 4096^2, +10 % on the PRO pass; superseded by the rings in the default build). With 8-byte
+    // accumulators the extra registers spill (-5 % at 2048^2 fp64): there the row is fetched at the start of its own step.
     constexpr bool PREFETCH = sizeof(A) == 4 && !C::template src_ring<R, A>();
     R pre[4] = {(R)0, (R)0, (R)0, (R)0}, pv[2] = {(R)0, (R)0};
     auto fetch = [&](const int q, const bool ok) {
